@@ -1,0 +1,128 @@
+/* rexsim.h -- C ABI of the B200-native batched Rex simulator (librexsim.so).
+ *
+ * Drop-in boundary for rex-gym's per-step hot path.  The reference has no FFI of its own for this
+ * path: its native boundary is pybullet's C-API reached through BulletClient.__getattr__
+ * (rex_gym/util/bullet_client.py:40-54), crossed ~265 times per env-step
+ * (rex_gym/model/rex.py:158-163,326-330,451,477,545).  Each entry point below replaces a whole
+ * group of those crossings for N environments at once:
+ *
+ *   rexsim_create   <- RexGymEnv.__init__ world setup: resetSimulation / setPhysicsEngineParameter /
+ *                      setTimeStep / loadURDF / setGravity      (rex_gym/envs/rex_gym_env.py:304-339)
+ *   rexsim_reset    <- BatchEnv.reset(indices) -> <task>.reset -> Rex.Reset (settle) + task draws
+ *                      (rex_gym/agents/tools/batch_env.py:92-109; rex_gym/model/rex.py:255-324;
+ *                       rex_gym/envs/gym/walk_env.py:125-154)
+ *   rexsim_step     <- BatchEnv.step(actions) -> RexGymEnv.step: signal -> Rex.Step x action_repeat
+ *                      (ApplyAction + stepSimulation + ReceiveObservation) -> reward/termination/obs
+ *                      (rex_gym/agents/tools/batch_env.py:63-90; rex_gym/envs/rex_gym_env.py:369-414)
+ *   rexsim_get_state / rexsim_set_state
+ *                   <- getBasePositionAndOrientation / getBaseVelocity / getJointState /
+ *                      resetBasePositionAndOrientation / resetJointState (rex_gym/model/rex.py:297-299,
+ *                      360-372,416,451,545) -- used for golden comparison and checkpoint/resume
+ *   rexsim_destroy  <- RexGymEnv.close (rex_gym/envs/rex_gym_env.py:287-291)
+ *
+ * Conventions: plain C, no exceptions; every function returns 0 or a negative RexSimStatus.
+ * All array arguments marked "dev" are DEVICE pointers owned by the caller; the library borrows them
+ * for the duration of the enqueue.  All work is enqueued on the cudaStream_t passed as `void* stream`
+ * (NULL = legacy default stream); nothing synchronises the host except rexsim_create.
+ * A handle is not re-entrant (one stream at a time).
+ */
+#ifndef REXSIM_H
+#define REXSIM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    REXSIM_OK = 0,
+    REXSIM_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    REXSIM_ERR_MODEL = -2,        /* model tables do not have the Rex leg structure the kernels assume */
+    REXSIM_ERR_CUDA = -3,         /* CUDA runtime error (see rexsim_last_error) */
+    REXSIM_ERR_UNSUPPORTED = -4,  /* valid reference configuration not built yet */
+} RexSimStatus;
+
+enum { REXSIM_TASK_WALK = 0, REXSIM_TASK_GALLOP = 1, REXSIM_TASK_TURN = 2, REXSIM_TASK_STANDUP = 3 };
+enum { REXSIM_SIGNAL_IK = 0, REXSIM_SIGNAL_OL = 1 };
+enum { REXSIM_TERRAIN_PLANE = 0, REXSIM_TERRAIN_RANDOM = 1 };
+
+/* per-env device error bits (rexsim_step ORs them into err_flags[env]) */
+enum {
+    REXSIM_FLAG_NONFINITE = 1,        /* non-finite state/obs/reward (ConvertTo32Bit raises, wrappers.py:522,542) */
+    REXSIM_FLAG_JOINT_LIMIT = 2,      /* a joint crossed its URDF limit: needs the joint-limit rows */
+    REXSIM_FLAG_BODY_CONTACT = 4,     /* a non-toe collision box reached the ground: needs the body rows */
+};
+
+#define REXSIM_MAX_TOE_PTS 32
+/* float offsets inside the model table (see rex_gym_b200/model_tables.py for the packer) */
+#define REXSIM_MT_BASE 0            /* mass, com[3], inertia[6](xx,yy,zz,xy,xz,yz), root_mass, root_inertia[3], pad[2] */
+#define REXSIM_MT_LEG 16            /* [4 legs][3 bodies][16]: jpos[3], mass, com[3], lower, inertia[6], upper, pad */
+#define REXSIM_MT_TOE (16 + 192)    /* [4 legs][REXSIM_MAX_TOE_PTS][3] toe hull sample points, foot-body frame */
+#define REXSIM_MT_BOX (16 + 192 + 384)         /* [4 legs][3 bodies][8 corners][3] collision box corners, body frame */
+#define REXSIM_MT_BASEBOX (16 + 192 + 384 + 288) /* [3 boxes][8][3] base + chassis boxes */
+#define REXSIM_MT_FLOATS (16 + 192 + 384 + 288 + 72)
+
+typedef struct {
+    int32_t num_envs;
+    int32_t task, signal, terrain;
+    int32_t num_motors;               /* 12 (mark 'base'); 18 ('arm') not built yet */
+    int32_t action_repeat;
+    int32_t solver_iterations;        /* int(300 / action_repeat) (rex_gym_env.py:25,184) */
+    float sim_dt;                     /* control_time_step / action_repeat (unused: sim_dt_d is authoritative) */
+    double sim_dt_d;
+    float motor_kp, motor_kd;
+    float kp_lo, kp_hi, kd_lo, kd_hi; /* per-env gains drawn at reset when lo != hi */
+    float target_position;            /* NaN: random per reset */
+    int32_t backwards;                /* -1 random, 0, 1 */
+    float target_orient, init_orient; /* NaN: random per reset */
+    float w_distance, w_energy, w_drift, w_shake;
+    int32_t normalize;                /* ClipAction + RangeNormalize fused (wrappers.py:183-265) */
+    int32_t max_episode_steps;        /* LimitDuration (wrappers.py:268-291), 0 = off */
+    int32_t auto_reset;               /* 1: done envs are reset at the end of rexsim_step; obs = reset obs */
+    uint64_t seed;
+    int32_t nfields;                  /* heightfield bank (terrain RANDOM) */
+    const float* fields;              /* dev [nfields][256*256], heights in metres (terrain.py:36-53) */
+    float friction;                   /* combined link x ground lateral friction */
+    float residual_threshold;         /* solver early-out (pybullet default 1e-7) */
+    float erp_contact, erp_joint;
+    int32_t toe_npts;                 /* valid points per toe in the model table */
+    float toe_margin;
+} RexSimConfig;
+
+typedef struct RexSim RexSim;
+
+/* observation / action widths for a task (no handle needed) */
+int rexsim_obs_dim(int32_t task, int32_t num_motors);
+int rexsim_action_dim(int32_t task, int32_t signal);
+/* words per env of the SoA state: float words, int words */
+int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int);
+
+/* model_tables: HOST pointer to REXSIM_MT_FLOATS floats.  Allocates device state, computes the settled
+ * reset snapshot(s) (600 physics sub-steps, rex.py:314-323) and synchronises. */
+int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_model_floats, RexSim** out);
+void rexsim_destroy(RexSim* sim);
+
+/* actions dev [N][A] f32; obs dev [N][O] f32; reward dev [N] f32; done dev [N] u8 */
+int rexsim_step(RexSim* sim, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
+/* idx dev [k] int32 (NULL: all envs, k ignored); obs_out dev [k][O] or NULL */
+int rexsim_reset(RexSim* sim, const int32_t* idx, int32_t k, float* obs_out, void* stream);
+
+/* Physical state of every env, SoA on device: out_f dev [13 + 2*nm][N] =
+ *   pos[3], quat[4] (x,y,z,w), linvel[3], angvel[3], q[nm], qd[nm];  out_i dev [4][N] =
+ *   step_counter, env_step_counter, flags, last-substep contact mask (bit l: toe l) */
+int rexsim_get_state(RexSim* sim, float* out_f, int32_t* out_i, void* stream);
+int rexsim_set_state(RexSim* sim, const float* in_f, void* stream);
+/* raw SoA state for checkpoint/resume: [n_float][N] f32 and [n_int][N] i32 device buffers */
+int rexsim_state_buffers(RexSim* sim, float** state_f, int32_t** state_i);
+/* dev [N + 1] int32: per-env error bits, then one word holding the OR of all; never cleared by the library */
+int rexsim_error_flags(RexSim* sim, int32_t** err_flags);
+/* last motor command of every env (info['action'], rex_gym_env.py:414): dev [nm][N] */
+int rexsim_last_command(RexSim* sim, float** cmd);
+/* kernels launched by this handle since create (the bench reports it) */
+int64_t rexsim_launch_count(const RexSim* sim);
+const char* rexsim_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

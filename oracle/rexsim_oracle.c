@@ -935,12 +935,14 @@ static void reset_env(RexoSim* s, int i) {
     RexoEnv* snap = &s->snapshot[field];
     double kp = c->kp_lo == c->kp_hi ? c->motor_kp : rand_uniform(s, i, rc, 4, c->kp_lo, c->kp_hi);
     double kd = c->kd_lo == c->kd_hi ? c->motor_kd : rand_uniform(s, i, rc, 5, c->kd_lo, c->kd_hi);
-    if (c->kp_lo == c->kp_hi && c->kd_lo == c->kd_hi) {
-        if (snap->reset_count == 0) { snap->field_id = field; snap->kp = kp; snap->kd = kd; settle_state(s, snap); snap->reset_count = 1; }
-        *e = *snap;
-    } else {   /* gains differ per env: the settle has to run per env */
-        e->field_id = field; e->kp = kp; e->kd = kd; settle_state(s, e);
+    /* the settle (rex.py:314-323) runs with the nominal gains; per-env randomised gains (ours, the
+     * reference ships no randomizer) apply from the first control step on, so the settled state only
+     * depends on (init pose, field) and is computed once per field */
+    if (snap->reset_count == 0) {
+        snap->field_id = field; snap->kp = c->motor_kp; snap->kd = c->motor_kd;
+        settle_state(s, snap); snap->reset_count = 1;
     }
+    *e = *snap;
     e->reset_count = rc; e->field_id = field; e->kp = kp; e->kd = kd;
     e->env_step_counter = 0; e->limit_step = 0;
     e->gp_phi = 0; e->gp_last_time = 0; e->gp_alpha = 0;

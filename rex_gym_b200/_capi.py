@@ -1,0 +1,73 @@
+"""ctypes binding of the C ABI in include/rexsim.h.  There is NO CPU fallback: if librexsim.so is
+missing or CUDA is unavailable the product path raises."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class RexSimConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("task", C.c_int32), ("signal", C.c_int32), ("terrain", C.c_int32),
+        ("num_motors", C.c_int32), ("action_repeat", C.c_int32), ("solver_iterations", C.c_int32),
+        ("sim_dt", C.c_float), ("sim_dt_d", C.c_double),
+        ("motor_kp", C.c_float), ("motor_kd", C.c_float),
+        ("kp_lo", C.c_float), ("kp_hi", C.c_float), ("kd_lo", C.c_float), ("kd_hi", C.c_float),
+        ("target_position", C.c_float), ("backwards", C.c_int32),
+        ("target_orient", C.c_float), ("init_orient", C.c_float),
+        ("w_distance", C.c_float), ("w_energy", C.c_float), ("w_drift", C.c_float), ("w_shake", C.c_float),
+        ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
+        ("seed", C.c_uint64), ("nfields", C.c_int32), ("fields", C.c_void_p),
+        ("friction", C.c_float), ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
+        ("toe_npts", C.c_int32), ("toe_margin", C.c_float),
+    ]
+
+
+EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
+           "rexsim_step", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
+           "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error"]
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(HERE, "librexsim.so")
+
+
+def load():
+    """Load librexsim.so (building it in-tree if the sources are newer).  Raises if impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if _build.needs_build():
+        _build.build()
+    L = C.CDLL(lib_path())
+    L.rexsim_obs_dim.argtypes = [C.c_int32, C.c_int32]
+    L.rexsim_action_dim.argtypes = [C.c_int32, C.c_int32]
+    L.rexsim_state_words.argtypes = [C.POINTER(RexSimConfig), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.rexsim_create.argtypes = [C.POINTER(RexSimConfig), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.rexsim_destroy.argtypes = [C.c_void_p]
+    L.rexsim_destroy.restype = None
+    L.rexsim_step.argtypes = [C.c_void_p] * 6
+    L.rexsim_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.rexsim_get_state.argtypes = [C.c_void_p] * 4
+    L.rexsim_set_state.argtypes = [C.c_void_p] * 3
+    L.rexsim_state_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.rexsim_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rexsim_last_command.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rexsim_launch_count.argtypes = [C.c_void_p]
+    L.rexsim_launch_count.restype = C.c_int64
+    L.rexsim_last_error.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().rexsim_last_error().decode()
+    if rc in (-1, -2, -4):
+        raise ValueError(f"rexsim: {msg} (status {rc})")
+    raise RuntimeError(f"rexsim: {msg} (status {rc})")

@@ -1,0 +1,185 @@
+// rexsim_capi.cu -- the C ABI declared in include/rexsim.h (plain pointers and sizes, no torch types).
+#include "rexsim_kernel.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+namespace rexsim {
+cudaError_t launch_step(const Params& P, cudaStream_t st);
+cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st);
+cudaError_t launch_settle(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st);
+cudaError_t launch_get_state(const Params& P, float* out_f, int32_t* out_i, cudaStream_t st);
+cudaError_t launch_set_state(const Params& P, const float* in_f, cudaStream_t st);
+}  // namespace rexsim
+
+using namespace rexsim;
+
+struct RexSim {
+    Params P;
+    float* d_model = nullptr;
+    float* d_sf = nullptr;
+    int32_t* d_si = nullptr;
+    float* d_snap_f = nullptr;
+    int32_t* d_snap_i = nullptr;
+    float* d_zoff = nullptr;
+    int32_t* d_err = nullptr;
+    float* d_cmd = nullptr;
+    int nsnap = 1;
+    int64_t launches = 0;
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+static int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return REXSIM_ERR_CUDA;
+}
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
+
+extern "C" {
+
+const char* rexsim_last_error(void) { return g_err; }
+
+int rexsim_obs_dim(int32_t task, int32_t num_motors) { return task == REXSIM_TASK_GALLOP ? 4 + num_motors : 4; }
+int rexsim_action_dim(int32_t task, int32_t signal) {
+    switch (task) {
+        case REXSIM_TASK_WALK: return signal == REXSIM_SIGNAL_IK ? 2 : 8;     /* walk_env.py:108-113 */
+        case REXSIM_TASK_GALLOP: return signal == REXSIM_SIGNAL_IK ? 2 : 4;   /* gallop_env.py:123-127 */
+        case REXSIM_TASK_TURN: return 2;                                      /* turn_env.py:104-108 */
+        default: return 1;                                                    /* standup_env.py:99 */
+    }
+}
+int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int) {
+    if (!cfg) return fail(REXSIM_ERR_INVALID, "null config");
+    if (n_float) *n_float = NF;
+    if (n_int) *n_int = NI;
+    return REXSIM_OK;
+}
+
+static int validate(const RexSimConfig* c) {
+    if (c->num_envs <= 0) return fail(REXSIM_ERR_INVALID, "num_envs must be positive");
+    if (c->task < 0 || c->task > 3 || c->signal < 0 || c->signal > 1) return fail(REXSIM_ERR_INVALID, "bad task/signal");
+    if (c->num_motors != 12) return fail(REXSIM_ERR_UNSUPPORTED, "mark='arm' (18 motors) is not built yet");
+    if (c->task == REXSIM_TASK_STANDUP) return fail(REXSIM_ERR_UNSUPPORTED, "standup needs the joint-limit/body-contact rows (not built yet)");
+    if (c->action_repeat <= 0 || c->solver_iterations <= 0 || !(c->sim_dt_d > 0)) return fail(REXSIM_ERR_INVALID, "bad time stepping");
+    if (c->terrain == REXSIM_TERRAIN_RANDOM && (c->nfields <= 0 || !c->fields)) return fail(REXSIM_ERR_INVALID, "random terrain needs a heightfield bank");
+    if (c->terrain != REXSIM_TERRAIN_PLANE && c->terrain != REXSIM_TERRAIN_RANDOM) return fail(REXSIM_ERR_UNSUPPORTED, "terrain type");
+    if (c->toe_npts <= 0 || c->toe_npts > REXSIM_MAX_TOE_PTS) return fail(REXSIM_ERR_MODEL, "toe_npts out of range");
+    return REXSIM_OK;
+}
+
+int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_model_floats, RexSim** out) {
+    if (!cfg || !model_tables || !out) return fail(REXSIM_ERR_INVALID, "null argument");
+    if (n_model_floats != REXSIM_MT_FLOATS) return fail(REXSIM_ERR_MODEL, "model table size mismatch");
+    int rc = validate(cfg);
+    if (rc) return rc;
+    RexSim* s = new RexSim();
+    memset(&s->P, 0, sizeof(Params));
+    s->P.cfg = *cfg;
+    s->P.cfg.sim_dt = (float)cfg->sim_dt_d;
+    const int N = cfg->num_envs;
+    s->P.N = N;
+    s->nsnap = cfg->terrain == REXSIM_TERRAIN_RANDOM ? cfg->nfields : 1;
+    CK(cudaMalloc(&s->d_model, REXSIM_MT_FLOATS * sizeof(float)));
+    CK(cudaMemcpy(s->d_model, model_tables, REXSIM_MT_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&s->d_sf, (size_t)NF * N * sizeof(float)));
+    CK(cudaMalloc(&s->d_si, (size_t)NI * N * sizeof(int32_t)));
+    CK(cudaMemset(s->d_sf, 0, (size_t)NF * N * sizeof(float)));
+    CK(cudaMemset(s->d_si, 0, (size_t)NI * N * sizeof(int32_t)));
+    CK(cudaMalloc(&s->d_snap_f, (size_t)NF * s->nsnap * sizeof(float)));
+    CK(cudaMalloc(&s->d_snap_i, (size_t)NI * s->nsnap * sizeof(int32_t)));
+    CK(cudaMemset(s->d_snap_f, 0, (size_t)NF * s->nsnap * sizeof(float)));
+    CK(cudaMemset(s->d_snap_i, 0, (size_t)NI * s->nsnap * sizeof(int32_t)));
+    CK(cudaMalloc(&s->d_err, (size_t)(N + 1) * sizeof(int32_t)));   /* [N] per-env bits + 1 word: OR of all */
+    CK(cudaMemset(s->d_err, 0, (size_t)(N + 1) * sizeof(int32_t)));
+    CK(cudaMalloc(&s->d_cmd, (size_t)12 * N * sizeof(float)));
+    CK(cudaMemset(s->d_cmd, 0, (size_t)12 * N * sizeof(float)));
+    if (cfg->terrain == REXSIM_TERRAIN_RANDOM) {
+        // vertical centring of each field: btHeightfieldTerrainShape local origin = (min+max)/2
+        std::vector<float> h((size_t)65536), zo(cfg->nfields);
+        for (int f = 0; f < cfg->nfields; f++) {
+            CK(cudaMemcpy(h.data(), cfg->fields + (size_t)f * 65536, 65536 * sizeof(float), cudaMemcpyDeviceToHost));
+            float lo = 1e30f, hi = -1e30f;
+            for (float v : h) { lo = fminf(lo, v); hi = fmaxf(hi, v); }
+            zo[f] = (float)(0.5 * ((double)lo + (double)hi));
+        }
+        CK(cudaMalloc(&s->d_zoff, cfg->nfields * sizeof(float)));
+        CK(cudaMemcpy(s->d_zoff, zo.data(), cfg->nfields * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    s->P.model = s->d_model; s->P.sf = s->d_sf; s->P.si = s->d_si;
+    s->P.snap_f = s->d_snap_f; s->P.snap_i = s->d_snap_i; s->P.field_zoff = s->d_zoff;
+    s->P.err = s->d_err; s->P.cmd_out = s->d_cmd;
+    // settled reset snapshots: Rex.Reset's 100 + 0.5/dt holding sub-steps (rex.py:314-323), once per field
+    for (int f = 0; f < s->nsnap; f++) {
+        s->P.settle_snapshot = f;
+        cudaError_t e = launch_settle(s->P, s->d_snap_f, s->d_snap_i, 0);
+        if (e != cudaSuccess) return cuda_fail(e, "settle launch");
+        s->launches++;
+    }
+    CK(cudaDeviceSynchronize());
+    *out = s;
+    return REXSIM_OK;
+}
+
+void rexsim_destroy(RexSim* s) {
+    if (!s) return;
+    cudaFree(s->d_model); cudaFree(s->d_sf); cudaFree(s->d_si); cudaFree(s->d_snap_f); cudaFree(s->d_snap_i);
+    cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd);
+    delete s;
+}
+
+int rexsim_step(RexSim* s, const float* actions, float* obs, float* reward, uint8_t* done, void* stream) {
+    if (!s || !actions || !obs || !reward || !done) return fail(REXSIM_ERR_INVALID, "null argument");
+    Params P = s->P;
+    P.actions = actions; P.obs = obs; P.reward = reward; P.done = done;
+    cudaError_t e = launch_step(P, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "step launch");
+    s->launches++;
+    return REXSIM_OK;
+}
+
+int rexsim_reset(RexSim* s, const int32_t* idx, int32_t k, float* obs_out, void* stream) {
+    if (!s) return fail(REXSIM_ERR_INVALID, "null handle");
+    if (idx && k < 0) return fail(REXSIM_ERR_INVALID, "negative count");
+    Params P = s->P;
+    P.reset_idx = idx; P.reset_k = k;
+    cudaError_t e = launch_reset(P, obs_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "reset launch");
+    if (!idx || k > 0) s->launches++;
+    return REXSIM_OK;
+}
+
+int rexsim_get_state(RexSim* s, float* out_f, int32_t* out_i, void* stream) {
+    if (!s || !out_f || !out_i) return fail(REXSIM_ERR_INVALID, "null argument");
+    cudaError_t e = launch_get_state(s->P, out_f, out_i, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "get_state launch");
+    s->launches++;
+    return REXSIM_OK;
+}
+int rexsim_set_state(RexSim* s, const float* in_f, void* stream) {
+    if (!s || !in_f) return fail(REXSIM_ERR_INVALID, "null argument");
+    cudaError_t e = launch_set_state(s->P, in_f, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "set_state launch");
+    s->launches++;
+    return REXSIM_OK;
+}
+int rexsim_state_buffers(RexSim* s, float** state_f, int32_t** state_i) {
+    if (!s) return fail(REXSIM_ERR_INVALID, "null handle");
+    if (state_f) *state_f = s->d_sf;
+    if (state_i) *state_i = s->d_si;
+    return REXSIM_OK;
+}
+int rexsim_error_flags(RexSim* s, int32_t** err_flags) {
+    if (!s || !err_flags) return fail(REXSIM_ERR_INVALID, "null argument");
+    *err_flags = s->d_err;
+    return REXSIM_OK;
+}
+int rexsim_last_command(RexSim* s, float** cmd) {
+    if (!s || !cmd) return fail(REXSIM_ERR_INVALID, "null argument");
+    *cmd = s->d_cmd;
+    return REXSIM_OK;
+}
+int64_t rexsim_launch_count(const RexSim* s) { return s ? s->launches : 0; }
+
+}  // extern "C"

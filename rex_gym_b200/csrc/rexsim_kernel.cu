@@ -1,0 +1,1080 @@
+// rexsim_kernel.cu -- sm_100a kernels: fused env step, reset, settle.  See rexsim_kernel.cuh for the design.
+#include "rexsim_kernel.cuh"
+#include <math.h>
+
+namespace rexsim {
+
+#define PI_F 3.14159265358979323846f
+#define PI_D 3.14159265358979323846
+
+// -------------------------------------------------------------------------------------------------
+// model tables: one 1-D TMA bulk copy global -> shared per CTA (cp.async.bulk + mbarrier)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_tables(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+    uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(gsrc), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar_a), "r"(0u) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// per-lane (leg) working set
+// -------------------------------------------------------------------------------------------------
+struct Lane {
+    // base (replicated on the 4 lanes of an env)
+    V3 pos; float qx, qy, qz, qw; V3 vl, w;
+    // own leg
+    float q[3], qd[3];
+    float tau_obs[3];
+    uint32_t ovh;          // 3 x 10-bit overheat counters
+    uint32_t enabled;      // 3 bits
+    int contact;           // own toe in contact during the last sub-step
+    int err;
+};
+
+__device__ __forceinline__ M3 quat_to_mat(float x, float y, float z, float w) {   // btMatrix3x3::setRotation
+    float d = x * x + y * y + z * z + w * w;
+    float s = 2.0f / d;
+    float xs = x * s, ys = y * s, zs = z * s;
+    float wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+    M3 R;
+    R.c0 = mk(1.f - (yy + zz), xy + wz, xz - wy);
+    R.c1 = mk(xy - wz, 1.f - (xx + zz), yz + wx);
+    R.c2 = mk(xz + wy, yz - wx, 1.f - (xx + yy));
+    return R;
+}
+__device__ __forceinline__ void quat_to_euler(float x, float y, float z, float w, float* rpy) {   // pybullet getEulerFromQuaternion
+    float sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
+    float sarg = -2.f * (x * z - w * y);
+    if (sarg <= -0.99999f) { rpy[0] = 0; rpy[1] = -0.5f * PI_F; rpy[2] = 2 * atan2f(x, -y); }
+    else if (sarg >= 0.99999f) { rpy[0] = 0; rpy[1] = 0.5f * PI_F; rpy[2] = 2 * atan2f(-x, y); }
+    else {
+        rpy[0] = atan2f(2 * (y * z + w * x), squ - sqx - sqy + sqz);
+        rpy[1] = asinf(sarg);
+        rpy[2] = atan2f(2 * (x * y + w * z), squ + sqx - sqy - sqz);
+    }
+}
+
+// 6x6 SPD inverse (symmetric storage m[i][j], i>=j used) via Cholesky, fully unrolled in registers
+struct Sym6 { float m[21]; };   // packed lower: idx(i,j) = i*(i+1)/2 + j
+__device__ __forceinline__ constexpr int ix(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+__device__ __forceinline__ Sym6 pack(const AI& I) {
+    Sym6 s;
+    s.m[ix(0, 0)] = I.A.xx; s.m[ix(1, 0)] = I.A.xy; s.m[ix(1, 1)] = I.A.yy; s.m[ix(2, 0)] = I.A.xz; s.m[ix(2, 1)] = I.A.yz; s.m[ix(2, 2)] = I.A.zz;
+    // lower-left block = B^T : element (3+j, i) = B[i][j]
+    s.m[ix(3, 0)] = I.b0.x; s.m[ix(3, 1)] = I.b1.x; s.m[ix(3, 2)] = I.b2.x;
+    s.m[ix(4, 0)] = I.b0.y; s.m[ix(4, 1)] = I.b1.y; s.m[ix(4, 2)] = I.b2.y;
+    s.m[ix(5, 0)] = I.b0.z; s.m[ix(5, 1)] = I.b1.z; s.m[ix(5, 2)] = I.b2.z;
+    s.m[ix(3, 3)] = I.D.xx; s.m[ix(4, 3)] = I.D.xy; s.m[ix(4, 4)] = I.D.yy; s.m[ix(5, 3)] = I.D.xz; s.m[ix(5, 4)] = I.D.yz; s.m[ix(5, 5)] = I.D.zz;
+    return s;
+}
+__device__ __forceinline__ Sym6 spd_inverse(const Sym6& A) {
+    float L[21];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        float s = A.m[ix(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) s = fmaf(-L[ix(j, k)], L[ix(j, k)], s);
+        float inv = rsqrtf(s);
+        // one Newton step keeps the factor at full fp32 accuracy
+        inv = inv * (1.5f - 0.5f * s * inv * inv);
+        L[ix(j, j)] = s * inv;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float t = A.m[ix(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) t = fmaf(-L[ix(i, k)], L[ix(j, k)], t);
+            L[ix(i, j)] = t * inv;
+        }
+    }
+    // Linv (lower)
+    float Li[21];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        Li[ix(j, j)] = 1.0f / L[ix(j, j)];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = j; k < i; k++) t = fmaf(-L[ix(i, k)], Li[ix(k, j)], t);
+            Li[ix(i, j)] = t / L[ix(i, i)];
+        }
+    }
+    Sym6 R;   // A^-1 = Li^T Li
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = i; k < 6; k++) t = fmaf(Li[ix(k, i)], Li[ix(k, j)], t);
+            R.m[ix(i, j)] = t;
+        }
+    return R;
+}
+__device__ __forceinline__ SV neg_mul(const Sym6& M, SV p) {   // -(M p)
+    float v[6] = {p.a.x, p.a.y, p.a.z, p.l.x, p.l.y, p.l.z}, o[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) t = fmaf(M.m[ix(i, j)], v[j], t);
+        o[i] = -t;
+    }
+    SV r; r.a = mk(o[0], o[1], o[2]); r.l = mk(o[3], o[4], o[5]);
+    return r;
+}
+
+// ground query --------------------------------------------------------------------------------------
+template <int TERRAIN>
+__device__ __forceinline__ void ground_query(const Params& P, int field, float zoff, V3 wp, float& dist, V3& n) {
+    if (TERRAIN == REXSIM_TERRAIN_PLANE) { dist = wp.z; n = mk(0.f, 0.f, 1.f); return; }
+    const float* h = P.cfg.fields + (size_t)field * 65536;
+    const float inv_cell = 20.0f;   // 1/0.05
+    float fx = fminf(fmaxf(wp.x * inv_cell + 127.5f, 0.f), 254.999f);
+    float fy = fminf(fmaxf(wp.y * inv_cell + 127.5f, 0.f), 254.999f);
+    int ixx = (int)floorf(fx), iyy = (int)floorf(fy);
+    float u = fx - ixx, v = fy - iyy;
+    float h00 = __ldg(h + iyy * 256 + ixx), h10 = __ldg(h + iyy * 256 + ixx + 1);
+    float h01 = __ldg(h + (iyy + 1) * 256 + ixx), h11 = __ldg(h + (iyy + 1) * 256 + ixx + 1);
+    float hx, hy;
+    if (v >= u) { hx = h11 - h01; hy = h01 - h00; } else { hx = h10 - h00; hy = h11 - h10; }
+    float hh = h00 + hx * u + hy * v - zoff;
+    float nx = -hx * inv_cell, ny = -hy * inv_cell;
+    float inv = rsqrtf(nx * nx + ny * ny + 1.f);
+    n = mk(nx * inv, ny * inv, inv);
+    dist = (wp.z - hh) * n.z;
+}
+__device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {   // btPlaneSpace1
+    if (fabsf(n.z) > 0.70710678118654752440f) {
+        float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+        p = mk(0.f, -n.z * k, n.y * k);
+        q = mk(a * k, -n.x * p.z, n.x * p.y);
+    } else {
+        float a = n.x * n.x + n.y * n.y, k = rsqrtf(a);
+        p = mk(-n.y * k, n.x * k, 0.f);
+        q = mk(-n.z * p.y, n.z * p.x, a * k);
+    }
+}
+
+// motor model + overheat (rex_gym/model/motor.py:76-143, rex_gym/model/rex.py:601-623) for one joint
+__device__ __forceinline__ float motor_torque(float cmd, float q, float qd, float kp, float kd, float& tau_obs) {
+    const float V = 32.0f, R = 0.186f, Kt = 0.0954f;
+    float pwm = -1.f * kp * (q - cmd) - kd * qd;
+    pwm = fminf(fmaxf(pwm, -1.f), 1.f);
+    tau_obs = fminf(fmaxf(Kt * (pwm * V / R), -5.7f), 5.7f);
+    float vnet = fminf(fmaxf(pwm * V - Kt * qd, -50.f), 50.f);
+    float cur = vnet / R;
+    float mag = fabsf(cur), t;
+    // np.interp over [0,10,...,60] -> [0,1,1.9,2.45,3.0,3.25,3.5]
+    if (mag >= 60.f) t = 3.5f;
+    else if (mag >= 50.f) t = 0.025f * (mag - 50.f) + 3.25f;
+    else if (mag >= 40.f) t = 0.025f * (mag - 40.f) + 3.0f;
+    else if (mag >= 30.f) t = 0.055f * (mag - 30.f) + 2.45f;
+    else if (mag >= 20.f) t = 0.055f * (mag - 20.f) + 1.9f;
+    else if (mag >= 10.f) t = 0.09f * (mag - 10.f) + 1.0f;
+    else t = 0.1f * mag;
+    return copysignf(t, cur) * (cur != 0.f ? 1.f : 0.f);
+}
+
+// -------------------------------------------------------------------------------------------------
+// one pybullet.stepSimulation for the 4 lanes of an env (call site rex_gym/model/rex.py:161)
+// -------------------------------------------------------------------------------------------------
+template <int TERRAIN>
+__device__ __forceinline__ void physics_substep(const Params& P, const float* __restrict__ sm, Lane& L, int leg,
+                                                const float* tau, int field, float zoff) {
+    const float dt = (float)P.cfg.sim_dt_d;
+    const float* LB = sm + REXSIM_MT_LEG + leg * 48;
+    // ---- forward kinematics, world-aligned frame with origin at the base position -------------------
+    M3 R0 = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
+    float s1, c1, s2, c2, s3, c3;
+    sincosf(L.q[0], &s1, &c1); sincosf(L.q[1], &s2, &c2); sincosf(L.q[2], &s3, &c3);
+    M3 R1; R1.c0 = R0.c0; R1.c1 = fma3(c1, R0.c1, s1 * R0.c2); R1.c2 = fma3(-s1, R0.c1, c1 * R0.c2);
+    M3 R2; R2.c0 = fma3(c2, R1.c0, -s2 * R1.c2); R2.c1 = R1.c1; R2.c2 = fma3(s2, R1.c0, c2 * R1.c2);
+    M3 R3; R3.c0 = fma3(c3, R2.c0, -s3 * R2.c2); R3.c1 = R2.c1; R3.c2 = fma3(s3, R2.c0, c3 * R2.c2);
+    V3 p1 = mul(R0, mk(LB[0], LB[1], LB[2]));
+    V3 p2 = p1 + mul(R1, mk(LB[16], LB[17], LB[18]));
+    V3 p3 = p2 + mul(R2, mk(LB[32], LB[33], LB[34]));
+    SV S1, S2, S3v;
+    S1.a = R0.c0; S1.l = cross(p1, S1.a);
+    S2.a = R1.c1; S2.l = cross(p2, S2.a);
+    S3v.a = R2.c1; S3v.l = cross(p3, S3v.a);
+    // ---- velocities and bias terms ------------------------------------------------------------------
+    SV v0; v0.a = L.w; v0.l = L.vl;
+    SV vj1 = L.qd[0] * S1, vj2 = L.qd[1] * S2, vj3 = L.qd[2] * S3v;
+    SV v1 = v0 + vj1, v2 = v1 + vj2, v3 = v2 + vj3;
+    SV cJ1 = crm(v1, vj1), cJ2 = crm(v2, vj2), cJ3 = crm(v3, vj3);
+    const float gz = -10.0f;   // setGravity(0,0,-10) rex_gym_env.py:314
+    AI IA1, IA2, IA3; SV pA1, pA2, pA3;
+    {
+        float m = LB[3]; V3 cw = p1 + mul(R1, mk(LB[4], LB[5], LB[6]));
+        S3 Ib = {LB[8], LB[9], LB[10], LB[11], LB[12], LB[13]};
+        IA1 = rigid_inertia(m, cw, rotate_inertia(R1, Ib));
+        pA1 = crf(v1, mul(IA1, v1));
+        pA1.a = pA1.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA1.l.z -= m * gz;
+    }
+    {
+        float m = LB[16 + 3]; V3 cw = p2 + mul(R2, mk(LB[16 + 4], LB[16 + 5], LB[16 + 6]));
+        S3 Ib = {LB[16 + 8], LB[16 + 9], LB[16 + 10], LB[16 + 11], LB[16 + 12], LB[16 + 13]};
+        IA2 = rigid_inertia(m, cw, rotate_inertia(R2, Ib));
+        pA2 = crf(v2, mul(IA2, v2));
+        pA2.a = pA2.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA2.l.z -= m * gz;
+    }
+    {
+        float m = LB[32 + 3]; V3 cw = p3 + mul(R3, mk(LB[32 + 4], LB[32 + 5], LB[32 + 6]));
+        S3 Ib = {LB[32 + 8], LB[32 + 9], LB[32 + 10], LB[32 + 11], LB[32 + 12], LB[32 + 13]};
+        IA3 = rigid_inertia(m, cw, rotate_inertia(R3, Ib));
+        pA3 = crf(v3, mul(IA3, v3));
+        pA3.a = pA3.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA3.l.z -= m * gz;
+    }
+    // ---- ABA inward pass over the own leg ------------------------------------------------------------
+    SV U3 = mul(IA3, S3v); float k3 = 1.0f / sdot(S3v, U3); float u3 = tau[2] - sdot(S3v, pA3);
+    rank1_sub(IA3, U3, k3);
+    pA3 = sfma(u3 * k3, U3, pA3 + mul(IA3, cJ3));
+    add(IA2, IA3); pA2 = pA2 + pA3;
+    SV U2 = mul(IA2, S2); float k2 = 1.0f / sdot(S2, U2); float u2 = tau[1] - sdot(S2, pA2);
+    rank1_sub(IA2, U2, k2);
+    pA2 = sfma(u2 * k2, U2, pA2 + mul(IA2, cJ2));
+    add(IA1, IA2); pA1 = pA1 + pA2;
+    SV U1 = mul(IA1, S1); float k1 = 1.0f / sdot(S1, U1); float u1 = tau[0] - sdot(S1, pA1);
+    rank1_sub(IA1, U1, k1);
+    pA1 = sfma(u1 * k1, U1, pA1 + mul(IA1, cJ1));
+    // ---- base: reduce the 4 legs, add the base body, invert ------------------------------------------
+    AI IA0; SV pA0;
+    {
+        const float* B = sm + REXSIM_MT_BASE;
+        float m = B[0]; V3 cw = mul(R0, mk(B[1], B[2], B[3]));
+        S3 Ib = {B[4], B[5], B[6], B[7], B[8], B[9]};
+        IA0 = rigid_inertia(m, cw, rotate_inertia(R0, Ib));
+        pA0 = crf(v0, mul(IA0, v0));
+        pA0.a = pA0.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA0.l.z -= m * gz;
+        // Bullet default base damping 0.04 (K1 = K2) with the un-merged root link's mass / inertia
+        const float kd = 0.04f;
+        V3 wb = mk(dot(R0.c0, L.w), dot(R0.c1, L.w), dot(R0.c2, L.w));
+        float wn = sqrtf(dot(wb, wb)), vn = sqrtf(dot(L.vl, L.vl));
+        V3 tb = mk(B[11] * wb.x, B[12] * wb.y, B[13] * wb.z);
+        pA0.a = fma3(kd + kd * wn, mul(R0, tb), pA0.a);
+        pA0.l = fma3(B[10] * (kd + kd * vn), L.vl, pA0.l);
+        AI Is;
+        Is.A.xx = sum4(IA1.A.xx); Is.A.yy = sum4(IA1.A.yy); Is.A.zz = sum4(IA1.A.zz);
+        Is.A.xy = sum4(IA1.A.xy); Is.A.xz = sum4(IA1.A.xz); Is.A.yz = sum4(IA1.A.yz);
+        Is.D.xx = sum4(IA1.D.xx); Is.D.yy = sum4(IA1.D.yy); Is.D.zz = sum4(IA1.D.zz);
+        Is.D.xy = sum4(IA1.D.xy); Is.D.xz = sum4(IA1.D.xz); Is.D.yz = sum4(IA1.D.yz);
+        Is.b0 = sum4(IA1.b0); Is.b1 = sum4(IA1.b1); Is.b2 = sum4(IA1.b2);
+        add(IA0, Is);
+        pA0 = pA0 + sum4(pA1);
+    }
+    Sym6 Minv = spd_inverse(pack(IA0));
+    SV a0 = neg_mul(Minv, pA0);
+    // ---- ABA outward pass ------------------------------------------------------------------------------
+    SV a1 = a0 + cJ1; float qdd1 = (u1 - sdot(U1, a1)) * k1; a1 = sfma(qdd1, S1, a1);
+    SV a2 = a1 + cJ2; float qdd2 = (u2 - sdot(U2, a2)) * k2; a2 = sfma(qdd2, S2, a2);
+    SV a3 = a2 + cJ3; float qdd3 = (u3 - sdot(U3, a3)) * k3;
+    // unconstrained velocities (btMultiBodyDynamicsWorld::solveConstraints: v += a*dt)
+    SV vs; vs.a = fma3(dt, a0.a, L.w); vs.l = fma3(dt, a0.l + cross(L.w, L.vl), L.vl);
+    float qs1 = fmaf(dt, qdd1, L.qd[0]), qs2 = fmaf(dt, qdd2, L.qd[1]), qs3 = fmaf(dt, qdd3, L.qd[2]);
+
+    // ---- toe / ground contact: deepest hull sample point ------------------------------------------------
+    const float* TP = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
+    float best = 1e30f; V3 rc = mk(0.f, 0.f, 0.f), nrm = mk(0.f, 0.f, 1.f);
+    const int npts = P.cfg.toe_npts;
+    for (int j = 0; j < npts; j++) {
+        V3 r = p3 + mul(R3, mk(TP[3 * j], TP[3 * j + 1], TP[3 * j + 2]));
+        float d; V3 n;
+        ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+        d -= P.cfg.toe_margin;
+        if (d < best) { best = d; rc = r; nrm = n; }
+    }
+    const bool active = best <= 0.0005f;
+    L.contact = active ? 1 : 0;
+    // ---- conditions this fast path does not model: flag loudly ------------------------------------------
+    {
+        int e = 0;
+        if (L.q[0] < LB[7] || L.q[0] > LB[14] || L.q[1] < LB[16 + 7] || L.q[1] > LB[16 + 14] || L.q[2] < LB[32 + 7] || L.q[2] > LB[32 + 14])
+            e |= REXSIM_FLAG_JOINT_LIMIT;
+        const float* BX = sm + REXSIM_MT_BOX + leg * 72;
+        float zmin = 1e30f;
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            float zc1 = p1.z + R1.c0.z * BX[3 * j] + R1.c1.z * BX[3 * j + 1] + R1.c2.z * BX[3 * j + 2];
+            float zc2 = p2.z + R2.c0.z * BX[24 + 3 * j] + R2.c1.z * BX[24 + 3 * j + 1] + R2.c2.z * BX[24 + 3 * j + 2];
+            float zc3 = p3.z + R3.c0.z * BX[48 + 3 * j] + R3.c1.z * BX[48 + 3 * j + 1] + R3.c2.z * BX[48 + 3 * j + 2];
+            zmin = fminf(zmin, fminf(zc1, fminf(zc2, zc3)));
+        }
+        const float* BB = sm + REXSIM_MT_BASEBOX + (leg % 3) * 24;   // lanes 0..2 check one base/chassis box each
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            float zc = R0.c0.z * BB[3 * j] + R0.c1.z * BB[3 * j + 1] + R0.c2.z * BB[3 * j + 2];
+            zmin = fminf(zmin, zc);
+        }
+        if (TERRAIN == REXSIM_TERRAIN_PLANE) { if (zmin + L.pos.z <= 0.0005f) e |= REXSIM_FLAG_BODY_CONTACT; }
+        else { if (zmin + L.pos.z <= 0.0005f + 0.03f) e |= REXSIM_FLAG_BODY_CONTACT; }
+        L.err |= e;
+    }
+    // any contact in this env?  (skip the solver in flight)
+    const unsigned act_mask = __ballot_sync(0xffffffffu, active);
+    const unsigned env_bits = (act_mask >> ((threadIdx.x & 31) & ~3)) & 0xFu;
+    float dq1 = 0.f, dq2 = 0.f, dq3 = 0.f; SV dv0; dv0.a = mk(0, 0, 0); dv0.l = mk(0, 0, 0);
+    if (act_mask != 0u) {
+        // ---- constraint rows of the own contact: n, t1, t2 ----------------------------------------------
+        V3 t1, t2;
+        if (TERRAIN == REXSIM_TERRAIN_PLANE) { t1 = mk(0.f, -1.f, 0.f); t2 = mk(1.f, 0.f, 0.f); }
+        else plane_space(nrm, t1, t2);
+        SV F[3];
+        F[0].a = cross(rc, nrm); F[0].l = nrm;
+        F[1].a = cross(rc, t1); F[1].l = t1;
+        F[2].a = cross(rc, t2); F[2].l = t2;
+        SV v3s = sfma(qs3, S3v, sfma(qs2, S2, sfma(qs1, S1, vs)));   // foot spatial velocity after the free update
+        float relv[3] = {sdot(F[0], v3s), sdot(F[1], v3s), sdot(F[2], v3s)};
+        // unit impulse responses of the own rows: inward along the leg, then the base solve
+        float uD1[3], uD2[3], uD3[3]; SV dvb[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            SV pD; pD.a = mk(-F[d].a.x, -F[d].a.y, -F[d].a.z); pD.l = mk(-F[d].l.x, -F[d].l.y, -F[d].l.z);
+            uD3[d] = -sdot(S3v, pD); pD = sfma(uD3[d] * k3, U3, pD);
+            uD2[d] = -sdot(S2, pD); pD = sfma(uD2[d] * k2, U2, pD);
+            uD1[d] = -sdot(S1, pD); pD = sfma(uD1[d] * k1, U1, pD);
+            dvb[d] = neg_mul(Minv, pD);
+        }
+        // Delassus rows A[r][3*s+d] = J_r M^-1 J_(s,d)^T : outward pass of every impulse through the own leg
+        float A[3][12];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                SV b = bcast4(dvb[d], s);
+                const bool own = (s == leg);
+                float e1 = ((own ? uD1[d] : 0.f) - sdot(U1, b)) * k1; b = sfma(e1, S1, b);
+                float e2 = ((own ? uD2[d] : 0.f) - sdot(U2, b)) * k2; b = sfma(e2, S2, b);
+                float e3 = ((own ? uD3[d] : 0.f) - sdot(U3, b)) * k3; b = sfma(e3, S3v, b);
+                A[0][3 * s + d] = sdot(F[0], b); A[1][3 * s + d] = sdot(F[1], b); A[2][3 * s + d] = sdot(F[2], b);
+            }
+        }
+        // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
+        float den[3], dinv[3], rhs[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float sel = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; s++) sel = (s == leg) ? A[d][3 * s + d] : sel;
+            den[d] = sel; dinv[d] = 1.0f / sel;
+        }
+        {
+            const float slop = 1e-5f;
+            float pen = best + slop;
+            float poserr = 0.f, velerr = -relv[0];
+            if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.cfg.erp_contact / dt;
+            rhs[0] = (pen > -0.04f) ? (poserr + velerr) * dinv[0] : velerr * dinv[0];
+            rhs[1] = -relv[1] * dinv[1];
+            rhs[2] = -relv[2] * dinv[2];
+        }
+        // ---- PGS in impulse space, Bullet row order: normals 0..3, then (t1,t2) of contacts 0..3 -----------
+        float lam[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) lam[j] = 0.f;
+        const float mu = P.cfg.friction, thr = P.cfg.residual_threshold;
+        const int iters = P.cfg.solver_iterations;
+        bool running = env_bits != 0u;   // env has at least one contact
+        for (int it = 0; it < iters; it++) {
+            if (!__any_sync(0xffffffffu, running)) break;
+            float resid = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                float dvn = 0.f;
+#pragma unroll
+                for (int j = 0; j < 12; j++) dvn = fmaf(A[0][j], lam[j], dvn);
+                float own = 0.f;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; s2++) own = (s2 == leg) ? lam[3 * s2] : own;
+                float dI = rhs[0] - dvn * dinv[0];
+                float sum = own + dI;
+                if (sum < 0.f) { dI = -own; sum = 0.f; }
+                const bool upd = running && active && (leg == s);
+                float nv = upd ? sum : own;
+                if (upd) { float rs = dI * den[0]; resid = fmaxf(resid, rs * rs); }
+                lam[3 * s] = bcast4(nv, s);
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+#pragma unroll
+                for (int d = 1; d < 3; d++) {
+                    float dvn = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 12; j++) dvn = fmaf(A[d][j], lam[j], dvn);
+                    float own = 0.f, tot = 0.f;
+#pragma unroll
+                    for (int s2 = 0; s2 < 4; s2++) { own = (s2 == leg) ? lam[3 * s2 + d] : own; tot = (s2 == leg) ? lam[3 * s2] : tot; }
+                    float dI = rhs[d] - dvn * dinv[d];
+                    float sum = own + dI;
+                    float lim = mu * tot;
+                    if (sum < -lim) { dI = -lim - own; sum = -lim; }
+                    else if (sum > lim) { dI = lim - own; sum = lim; }
+                    const bool upd = running && active && (leg == s) && (tot > 0.f);
+                    float nv = upd ? sum : own;
+                    if (upd) { float rs = dI * den[d]; resid = fmaxf(resid, rs * rs); }
+                    lam[3 * s + d] = bcast4(nv, s);
+                }
+            }
+            resid = max4(resid);
+            if (resid <= thr) running = false;
+        }
+        // ---- apply the net contact impulse: one more response pass -----------------------------------------
+        float ln = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; s2++) { ln = (s2 == leg) ? lam[3 * s2] : ln; l1 = (s2 == leg) ? lam[3 * s2 + 1] : l1; l2 = (s2 == leg) ? lam[3 * s2 + 2] : l2; }
+        float e1 = ln * uD1[0] + l1 * uD1[1] + l2 * uD1[2];
+        float e2 = ln * uD2[0] + l1 * uD2[1] + l2 * uD2[2];
+        float e3 = ln * uD3[0] + l1 * uD3[1] + l2 * uD3[2];
+        SV own_b = sfma(ln, dvb[0], sfma(l1, dvb[1], l2 * dvb[2]));
+        dv0 = sum4(own_b);
+        SV b = dv0;
+        dq1 = (e1 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
+        dq2 = (e2 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
+        dq3 = (e3 - sdot(U3, b)) * k3;
+    }
+    // ---- integrate (btMultiBody::stepPositionsMultiDof) --------------------------------------------------
+    L.w = vs.a + dv0.a; L.vl = vs.l + dv0.l;
+    L.qd[0] = qs1 + dq1; L.qd[1] = qs2 + dq2; L.qd[2] = qs3 + dq3;
+    L.pos = fma3(dt, L.vl, L.pos);
+    L.q[0] = fmaf(dt, L.qd[0], L.q[0]); L.q[1] = fmaf(dt, L.qd[1], L.q[1]); L.q[2] = fmaf(dt, L.qd[2], L.q[2]);
+    {
+        float fa = sqrtf(dot(L.w, L.w));
+        if (fa * dt > 0.7853981633974483f) fa = 0.5f * 1.5707963267948966f / dt;
+        float sc;
+        if (fa < 0.001f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * fa * fa;
+        else sc = sinf(0.5f * fa * dt) / fa;
+        float ax = L.w.x * sc, ay = L.w.y * sc, az = L.w.z * sc, aw = cosf(fa * dt * 0.5f);
+        float nw = aw * L.qw - ax * L.qx - ay * L.qy - az * L.qz;
+        float nx = aw * L.qx + ax * L.qw + ay * L.qz - az * L.qy;
+        float ny = aw * L.qy - ax * L.qz + ay * L.qw + az * L.qx;
+        float nz = aw * L.qz + ax * L.qy - ay * L.qx + az * L.qw;
+        float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+        L.qx = nx * inv; L.qy = ny * inv; L.qz = nz * inv; L.qw = nw * inv;
+    }
+}
+
+// Rex.ApplyAction + stepSimulation (rex_gym/model/rex.py:158-163,568-641) for the own leg's three motors
+template <int TERRAIN>
+__device__ __forceinline__ void apply_action_and_step(const Params& P, const float* sm, Lane& L, int leg,
+                                                      const float* cmd, float kp, float kd, int field, float zoff) {
+    float tau[3];
+    const uint32_t limit = (uint32_t)(1.0 / P.cfg.sim_dt_d);   // OVERHEAT_SHUTDOWN_TIME / time_step
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float to;
+        float ta = motor_torque(cmd[j], L.q[j], L.qd[j], kp, kd, to);
+        uint32_t c = (L.ovh >> (10 * j)) & 1023u;
+        c = (fabsf(ta) > 2.45f) ? min(c + 1u, 1023u) : 0u;
+        if (c > limit) L.enabled &= ~(1u << j);
+        L.ovh = (L.ovh & ~(1023u << (10 * j))) | (c << (10 * j));
+        L.tau_obs[j] = to;
+        tau[j] = ((L.enabled >> j) & 1u) ? ta : 0.f;
+    }
+    physics_substep<TERRAIN>(P, sm, L, leg, tau, field, zoff);
+}
+
+// -------------------------------------------------------------------------------------------------
+// gait planner + IK for the own leg (model/gait_planner.py:31-134, model/kinematics.py:80-142)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bezier_sums(float phi, float& SX, float& SZ) {   // sum_k C(11,k) phi^k (1-phi)^(11-k) P_k, k<10
+    const float BX[10] = {-0.04f, -0.056f, -0.06f, -0.06f, -0.06f, 0.f, 0.f, 0.f, 0.06f, 0.06f};
+    const float BZ[10] = {0.f, 0.f, 0.0405f, 0.0405f, 0.0405f, 0.0405f, 0.0405f, 0.0495f, 0.0495f, 0.0495f};
+    const float BIN[10] = {1.f, 11.f, 55.f, 165.f, 330.f, 462.f, 462.f, 330.f, 165.f, 55.f};
+    float om = 1.f - phi;
+    float pw[12], qw[12];
+    pw[0] = 1.f; qw[0] = 1.f;
+#pragma unroll
+    for (int k = 1; k < 12; k++) { pw[k] = pw[k - 1] * phi; qw[k] = qw[k - 1] * om; }
+    SX = 0.f; SZ = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; k++) { float b = BIN[k] * pw[k] * qw[11 - k]; SX = fmaf(BX[k], b, SX); SZ = fmaf(BZ[k], b, SZ); }
+}
+// step contribution (long or rot) given phase data; angle in degrees
+__device__ __forceinline__ V3 step_part(bool stance, float phase, float SX, float SZ, float v, float angle_deg, float direction) {
+    float s, c; sincosf(angle_deg * (PI_F / 180.0f), &s, &c);
+    float av = fabsf(v);
+    if (stance) {
+        float p = 0.05f * (1.f - 2.f * phase);
+        return mk(c * p * av, -s * p * av, -0.001f * cosf(PI_F / (2.f * 0.05f) * p));
+    }
+    float X = av * c * direction;           // X_i = |v| c BX_i dir
+    return mk(X * SX, av * s * (-X) * SX, av * SZ);
+}
+__device__ __forceinline__ void solve_ik_leg(V3 c, bool right, float* ang) {
+    const float hip = 0.055f, leg = 0.10652f, foot = 0.145f;
+    float dom = (c.y * c.y + c.z * c.z - hip * hip + c.x * c.x - leg * leg - foot * foot) / (2.f * foot * leg);
+    if (dom > 1.f || dom < -1.f) dom = dom > 1.f ? 0.99f : -0.99f;
+    float gamma = atan2f(-sqrtf(1.f - dom * dom), dom);
+    float sq = c.y * c.y + c.z * c.z - hip * hip;
+    if (sq < 0.f) sq = 0.f;
+    float sg, cg; sincosf(gamma, &sg, &cg);
+    float alpha = atan2f(-c.x, sqrtf(sq)) - atan2f(foot * sg, leg + foot * cg);
+    float hv = right ? -hip : hip;
+    float theta = -atan2f(c.z, c.y) - atan2f(sqrtf(sq), hv);
+    ang[0] = theta; ang[1] = -alpha; ang[2] = -gamma;
+}
+
+struct GaitState { double phi; int last_step; float alpha; };
+
+// GaitPlanner.loop + Kinematics.solve for the own leg; il = IK leg index (FR,FL,RR,RL) = lane ^ 1
+template <bool ROT>
+__device__ __forceinline__ void ik_signal(GaitState& G, bool gallop, int step_counter, double dtd, int leg,
+                                          float base_x, float base_z, float v, float w_rot, double T, float direction, float* cmd) {
+    const int il = leg ^ 1;
+    double now = step_counter * dtd;
+    if (T <= 0.01) T = 0.01;
+    if (G.phi >= 0.99) G.last_step = step_counter;
+    G.phi = (now - G.last_step * dtd) / T;
+    double off = gallop ? ((il >= 2) ? 0.8 : 0.0) : ((il == 1 || il == 2) ? 0.5 : 0.0);
+    double ph = G.phi + off;
+    if (ph >= 1) ph = ph - 1.;
+    const bool stance = ph <= 0.5;
+    float phase = stance ? (float)(ph / 0.5) : (float)((ph - 0.5) / (1 - 0.5));
+    float SX = 0.f, SZ = 0.f;
+    if (!stance) bezier_sums(phase, SX, SZ);
+    const float fx = (il < 2) ? 0.115f : -0.115f, fy = (il & 1) ? 0.0925f : -0.0925f, fz = -0.2f;
+    V3 lg = step_part(stance, phase, SX, SZ, v, 0.f, direction);
+    V3 rt;
+    if (ROT) {
+        // legs update the shared alpha serially in IK order FR, FL, RR, RL (gait_planner.py:66-89)
+        const float r = sqrtf(fx * fx + fy * fy);
+        const float foot_angle = atan2f(fy, fx);
+        float alpha = G.alpha;
+        rt = mk(0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float circle = (w_rot >= 0.f ? 90.f : 270.f) - (foot_angle - alpha) * (180.0f / PI_F);
+            V3 cand = step_part(stance, phase, SX, SZ, w_rot, circle, direction);
+            float mag = atan2f(sqrtf(cand.x * cand.x + cand.y * cand.y), r);
+            float na = (fy > 0.f) ? ((cand.x < 0.f) ? -mag : mag) : ((cand.x < 0.f) ? mag : -mag);
+            if (il == k) rt = cand;
+            alpha = bcast4(na, k ^ 1);
+        }
+        G.alpha = alpha;
+    } else {
+        rt = mk(0.f, 0.f, stance ? -0.001f * cosf(PI_F / (2.f * 0.05f) * (0.05f * (1.f - 2.f * phase))) : 0.f);
+    }
+    // Kinematics.solve with zero orientation: hip = HIP + pos; coord = foot - hip; t = coord - pos
+    V3 frame = mk(fx + lg.x + rt.x, fy + lg.y + rt.y, fz + lg.z + rt.z);
+    V3 hipv = mk(((il < 2) ? 0.115f : -0.115f) + base_x, ((il & 1) ? 0.0375f : -0.0375f), 0.f + base_z);
+    V3 c = frame - hipv;
+    V3 tc = mk(c.x - base_x, c.y, c.z - base_z);
+    solve_ik_leg(tc, (il & 1) == 0, cmd);
+}
+
+__constant__ float c_pose_stand[3] = {0.f, -0.88643435f, 1.30197369f};
+__constant__ float c_pose_stand_ol[3] = {0.15192765f, -0.90412283f, 1.48156545f};   // sign of [0] alternates per leg
+
+__device__ __forceinline__ void init_pose(int signal, int leg, float* p) {
+    if (signal == REXSIM_SIGNAL_OL) { p[0] = (leg & 1) ? -c_pose_stand_ol[0] : c_pose_stand_ol[0]; p[1] = c_pose_stand_ol[1]; p[2] = c_pose_stand_ol[2]; }
+    else { p[0] = c_pose_stand[0]; p[1] = c_pose_stand[1]; p[2] = c_pose_stand[2]; }
+}
+
+// per-env task bookkeeping (replicated on the 4 lanes)
+struct Task {
+    int step_counter, env_step, flags, end_step;
+    float target, torient, iorient;
+    GaitState G;
+};
+
+// <task>._transform_action_to_motor_command for the own leg
+template <int TASK, int SIGNAL>
+__device__ __forceinline__ void task_command(const Params& P, Task& K, const Lane& L, int leg, const float* act, float* cmd) {
+    const double dtd = P.cfg.sim_dt_d;
+    const double t = K.step_counter * dtd;
+    float ip[3]; init_pose(SIGNAL, leg, ip);
+    if (TASK == REXSIM_TASK_WALK) {                                   // envs/gym/walk_env.py:207-324
+        if (K.flags & FL_STILL) { cmd[0] = ip[0]; cmd[1] = ip[1]; cmd[2] = ip[2]; return; }
+        if (K.target != 0.f) {
+            if (fabsf(L.pos.x) >= fabsf(K.target) - 0.15f) {
+                K.flags |= FL_GOAL;
+                if (!(K.flags & FL_TERMINATING)) { K.end_step = K.step_counter; K.flags |= FL_TERMINATING; }
+            }
+        }
+        const double end_t = K.end_step * dtd;
+        if (SIGNAL == REXSIM_SIGNAL_IK) {
+            double p = 0.8 + (double)act[0];
+            double gait = (0.0 <= t && t <= p) ? t : 1.0;
+            double step = 0.6, period = 0.65; float base_x = 0.01f;
+            if (K.flags & FL_BACKWARDS) { step = -.3; period = .5; base_x = 0.f; }
+            double sl = step * gait;
+            if (K.flags & FL_GOAL) {
+                double pb = 0.8 + (double)act[1];
+                double brakes = (end_t <= t && t <= pb + end_t) ? 1 - (t - end_t) : 0.0;
+                sl *= brakes;
+                if (brakes == 0.0) K.flags |= FL_STILL;
+            }
+            float direction = sl < 0 ? -1.f : 1.f;
+            ik_signal<false>(K.G, false, K.step_counter, dtd, leg, base_x, 0.f, (float)sl, 0.f, period, direction, cmd);
+        } else {
+            double l_a = 0.1, f_a = 0.2;
+            if (K.flags & FL_GOAL) {
+                double coeff = (end_t <= t && t <= 0.8 + end_t) ? 1 - (t - end_t) : 0.0;
+                l_a *= coeff; f_a *= coeff;
+                if (coeff == 0.0) K.flags |= FL_STILL;
+            }
+            double start = (0.0 <= t && t <= 0.8) ? t : 1.0;
+            l_a *= start; f_a *= start;
+            double cs = cos(2 * PI_D / (1.0 / 8) * t);
+            float l_ext = (float)(l_a * cs), f_ext = (float)(f_a * cs);
+            const bool diag = (leg == 0 || leg == 3);     // FL and RR extend, FR and RL swing
+            cmd[0] = ip[0];
+            cmd[1] = ip[1] + ((diag ? l_ext : -l_ext) + act[2 * leg]);
+            cmd[2] = ip[2] + ((diag ? f_ext : -f_ext) + act[2 * leg + 1]);
+        }
+    } else if (TASK == REXSIM_TASK_GALLOP) {                          // envs/gym/gallop_env.py:212-313
+        if (K.flags & FL_STILL) { cmd[0] = c_pose_stand[0]; cmd[1] = c_pose_stand[1]; cmd[2] = c_pose_stand[2]; return; }
+        if (K.target != 0.f) {
+            if (fabsf(L.pos.x) >= fabsf(K.target)) {
+                K.flags |= FL_GOAL;
+                if (!(K.flags & FL_TERMINATING)) { K.end_step = K.step_counter; K.flags |= FL_TERMINATING; }
+            }
+        }
+        const double end_t = K.end_step * dtd;
+        if (SIGNAL == REXSIM_SIGNAL_IK) {
+            double p = 1. + (double)act[1];
+            double gait = (0.0 <= t && t <= p) ? t : 1.0;
+            double sl = 1.3 * gait;
+            if (K.flags & FL_GOAL) {
+                double pb = 1. + (double)act[0];
+                double brakes = (end_t <= t && t <= pb + end_t) ? 1 - (t - end_t) : 0.0;
+                sl *= brakes;
+            }
+            ik_signal<false>(K.G, true, K.step_counter, dtd, leg, 0.01f, -0.007f, (float)sl, 0.f, 0.3, 1.f, cmd);
+        } else {
+            float a0 = act[(leg < 2) ? 0 : 2], a1 = act[(leg < 2) ? 1 : 3];
+            if (K.flags & FL_GOAL) {
+                double coeff = (end_t <= t && t <= 1. + end_t) ? 1 - (t - end_t) : 0.0;
+                a0 = (float)((double)a0 * coeff); a1 = (float)((double)a1 * coeff);
+                if (coeff == 0.0) K.flags |= FL_STILL;
+            }
+            cmd[0] = ip[0]; cmd[1] = ip[1] + a0; cmd[2] = ip[2] + a1;
+        }
+    } else if (TASK == REXSIM_TASK_TURN) {                            // envs/gym/turn_env.py:230-346
+        if (K.flags & FL_STILL) {
+            if (t - K.end_step * dtd >= 1.) K.flags |= FL_ENVGOAL;
+            cmd[0] = ip[0]; cmd[1] = ip[1]; cmd[2] = ip[2];
+            return;
+        }
+        {
+            float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
+            float cz = rpy[2];
+            if (cz < 0.f) cz += 6.28f;
+            if (fabsf(K.torient - cz) <= 0.01f) {
+                K.flags |= FL_GOAL;
+                if (!(K.flags & FL_TERMINATING)) { K.end_step = K.step_counter; K.flags |= FL_TERMINATING; }
+            }
+        }
+        if (SIGNAL == REXSIM_SIGNAL_IK) {
+            double gait = (0.0 <= t && t <= .8) ? t : 1.0;
+            double dirv = -0.5 * gait;
+            if (K.flags & FL_CLOCKWISE) dirv *= -1;
+            float step_rotation = (float)(dirv + (double)act[0]);
+            double step_period = 0.75 + (double)act[1];
+            if (K.flags & FL_GOAL) K.flags |= FL_STILL;
+            ik_signal<true>(K.G, false, K.step_counter, dtd, leg, 0.009f, 0.f, 0.02f, step_rotation, step_period, 1.f, cmd);
+        } else {
+            if (K.flags & FL_GOAL) K.flags |= FL_STILL;
+            const float extension = 0.1f, swing = 0.03f + act[0], swipe = 0.05f + act[1];
+            int ith = ((int)(t / (1.0 / 10.0))) % 2;
+            const bool cw = (K.flags & FL_CLOCKWISE) != 0;
+            // pose tables of turn_env.py:281-298, row = leg
+            const float sgn = ((leg == 0 || leg == 3) ? 1.f : -1.f) * (cw ? 1.f : -1.f);
+            float o0, o1, o2;
+            if (!ith) { o0 = (leg & 1) ? -swipe : swipe; o1 = (leg < 2) ? extension : -extension; o2 = sgn * swing; }
+            else { o0 = (leg & 1) ? swipe : -swipe; o1 = 0.f; o2 = -sgn * swing; }
+            float so[3]; init_pose(REXSIM_SIGNAL_OL, leg, so);
+            cmd[0] = so[0] + o0; cmd[1] = so[1] + o1; cmd[2] = so[2] + o2;
+        }
+    } else {                                                          // envs/gym/standup_env.py:113-134
+        if (t > 0.1) { cmd[0] = c_pose_stand[0]; cmd[1] = c_pose_stand[1]; cmd[2] = c_pose_stand[2]; return; }
+        double tt = t + 1;
+        float sc = (float)((.1 + (double)act[0]) / tt + 1.5);
+        cmd[0] = c_pose_stand[0] * sc; cmd[1] = c_pose_stand[1] * sc; cmd[2] = c_pose_stand[2] * sc;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// state load / store (SoA, coalesced across envs)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_lane(const float* sf, const int32_t* si, int N, int env, int leg, Lane& L) {
+    L.pos = mk(sf[(F_POS + 0) * (size_t)N + env], sf[(F_POS + 1) * (size_t)N + env], sf[(F_POS + 2) * (size_t)N + env]);
+    L.qx = sf[(F_QUAT + 0) * (size_t)N + env]; L.qy = sf[(F_QUAT + 1) * (size_t)N + env];
+    L.qz = sf[(F_QUAT + 2) * (size_t)N + env]; L.qw = sf[(F_QUAT + 3) * (size_t)N + env];
+    L.vl = mk(sf[(F_LINVEL + 0) * (size_t)N + env], sf[(F_LINVEL + 1) * (size_t)N + env], sf[(F_LINVEL + 2) * (size_t)N + env]);
+    L.w = mk(sf[(F_ANGVEL + 0) * (size_t)N + env], sf[(F_ANGVEL + 1) * (size_t)N + env], sf[(F_ANGVEL + 2) * (size_t)N + env]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        L.q[j] = sf[(F_Q + 3 * leg + j) * (size_t)N + env];
+        L.qd[j] = sf[(F_QD + 3 * leg + j) * (size_t)N + env];
+        L.tau_obs[j] = 0.f;
+    }
+    L.ovh = (uint32_t)si[(I_OVH + leg) * (size_t)N + env];
+    L.enabled = ((uint32_t)si[I_FLAGS * (size_t)N + env] >> (FL_ENABLED_SHIFT + 3 * leg)) & 7u;
+    L.contact = 0; L.err = 0;
+}
+__device__ __forceinline__ void load_task(const float* sf, const int32_t* si, int N, int env, Task& K) {
+    K.step_counter = si[I_STEP * (size_t)N + env];
+    K.env_step = si[I_ENVSTEP * (size_t)N + env];
+    K.flags = si[I_FLAGS * (size_t)N + env];
+    K.end_step = si[I_ENDSTEP * (size_t)N + env];
+    K.G.last_step = si[I_GPLAST * (size_t)N + env];
+    K.G.phi = __hiloint2double(si[I_PHI_HI * (size_t)N + env], si[I_PHI_LO * (size_t)N + env]);
+    K.G.alpha = sf[F_ALPHA * (size_t)N + env];
+    K.target = sf[F_TARGET * (size_t)N + env];
+    K.torient = sf[F_TORIENT * (size_t)N + env];
+    K.iorient = sf[F_IORIENT * (size_t)N + env];
+}
+__device__ __forceinline__ void store_lane(float* sf, int32_t* si, int N, int env, int leg, const Lane& L, const Task& K, bool valid) {
+    // shuffles first (all lanes participate), stores predicated on `valid`
+    uint32_t en = L.enabled << (3 * leg);
+    en |= __shfl_xor_sync(0xffffffffu, en, 1, 4); en |= __shfl_xor_sync(0xffffffffu, en, 2, 4);
+    uint32_t ct = (uint32_t)L.contact << leg;
+    ct |= __shfl_xor_sync(0xffffffffu, ct, 1, 4); ct |= __shfl_xor_sync(0xffffffffu, ct, 2, 4);
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        sf[(F_Q + 3 * leg + j) * (size_t)N + env] = L.q[j];
+        sf[(F_QD + 3 * leg + j) * (size_t)N + env] = L.qd[j];
+    }
+    si[(I_OVH + leg) * (size_t)N + env] = (int32_t)L.ovh;
+    if (leg == 0) {
+        sf[(F_POS + 0) * (size_t)N + env] = L.pos.x; sf[(F_POS + 1) * (size_t)N + env] = L.pos.y; sf[(F_POS + 2) * (size_t)N + env] = L.pos.z;
+        sf[(F_QUAT + 0) * (size_t)N + env] = L.qx; sf[(F_QUAT + 1) * (size_t)N + env] = L.qy;
+        sf[(F_QUAT + 2) * (size_t)N + env] = L.qz; sf[(F_QUAT + 3) * (size_t)N + env] = L.qw;
+        sf[(F_LINVEL + 0) * (size_t)N + env] = L.vl.x; sf[(F_LINVEL + 1) * (size_t)N + env] = L.vl.y; sf[(F_LINVEL + 2) * (size_t)N + env] = L.vl.z;
+        sf[(F_ANGVEL + 0) * (size_t)N + env] = L.w.x; sf[(F_ANGVEL + 1) * (size_t)N + env] = L.w.y; sf[(F_ANGVEL + 2) * (size_t)N + env] = L.w.z;
+        sf[F_ALPHA * (size_t)N + env] = K.G.alpha;
+        sf[F_TARGET * (size_t)N + env] = K.target;
+        si[I_STEP * (size_t)N + env] = K.step_counter;
+        si[I_ENVSTEP * (size_t)N + env] = K.env_step;
+        si[I_FLAGS * (size_t)N + env] = (K.flags & ((1 << FL_ENABLED_SHIFT) - 1)) | (int32_t)(en << FL_ENABLED_SHIFT);
+        si[I_ENDSTEP * (size_t)N + env] = K.end_step;
+        si[I_GPLAST * (size_t)N + env] = K.G.last_step;
+        si[I_PHI_HI * (size_t)N + env] = __double2hiint(K.G.phi);
+        si[I_PHI_LO * (size_t)N + env] = __double2loint(K.G.phi);
+        si[I_CONTACT * (size_t)N + env] = (int32_t)ct;
+    }
+}
+
+// reset one env from the settled snapshot + task draws (BatchEnv.reset -> <task>.reset; rex.py:255-324)
+__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field) {
+    const RexSimConfig& c = P.cfg;
+    const int N = P.N;
+    uint32_t rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env] + 1u;
+    field = (c.terrain == REXSIM_TERRAIN_RANDOM) ? (int)(((uint32_t)env + rc) % (uint32_t)c.nfields) : 0;
+    const float* sf = P.snap_f + (size_t)field * NF;
+    const int32_t* si = P.snap_i + (size_t)field * NI;
+    load_lane(sf, si, 1, 0, leg, L);
+    load_task(sf, si, 1, 0, K);
+    K.step_counter = 0; K.env_step = 0; K.end_step = 0;
+    K.flags = K.flags & ~((1 << FL_ENABLED_SHIFT) - 1);
+    K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
+    K.target = 0.f; K.torient = 0.f; K.iorient = 0.f;
+    kp = (c.kp_lo == c.kp_hi) ? c.motor_kp : (float)rand_uniform(c.seed, env, rc, 4, c.kp_lo, c.kp_hi);
+    kd = (c.kd_lo == c.kd_hi) ? c.motor_kd : (float)rand_uniform(c.seed, env, rc, 5, c.kd_lo, c.kd_hi);
+    if (c.task == REXSIM_TASK_WALK) {
+        int bw = (c.backwards < 0) ? (int)(rand_u32(c.seed, env, rc, 0) >> 31) : c.backwards;
+        if (bw) K.flags |= FL_BACKWARDS;
+        if (isnan(c.target_position)) K.target = (float)rand_uniform(c.seed, env, rc, 1, bw ? -2.0 : 1.0, bw ? -3.0 : 3.0);
+        else K.target = c.target_position;
+    } else if (c.task == REXSIM_TASK_GALLOP) {
+        K.target = isnan(c.target_position) ? (float)rand_uniform(c.seed, env, rc, 1, 1.0, 3.0) : c.target_position;
+    } else if (c.task == REXSIM_TASK_TURN) {
+        double to = isnan(c.target_orient) ? rand_uniform(c.seed, env, rc, 2, 0.2, 6.0) : (double)c.target_orient;
+        double io = isnan(c.init_orient) ? rand_uniform(c.seed, env, rc, 3, 0.2, 6.0) : (double)c.init_orient;
+        K.torient = (float)to; K.iorient = (float)io;
+        double diff = fabs(io - to);
+        bool cw = false;
+        if (io < to) { if (diff > 3.14) cw = true; } else { if (diff < 3.14) cw = true; }
+        if (cw) K.flags |= FL_CLOCKWISE;
+        L.pos = mk(0.f, 0.f, 0.21f);
+        float hy = (float)(io * 0.5);
+        L.qx = 0.f; L.qy = 0.f; L.qz = sinf(hy); L.qw = cosf(hy);
+    }
+    if (leg == 0) {
+        P.si[I_RESETCNT * (size_t)N + env] = (int32_t)rc;
+        P.si[I_FIELD * (size_t)N + env] = field;
+        P.sf[F_KP * (size_t)N + env] = kp; P.sf[F_KD * (size_t)N + env] = kd;
+        P.sf[F_TORIENT * (size_t)N + env] = K.torient; P.sf[F_IORIENT * (size_t)N + env] = K.iorient;
+    }
+}
+
+__device__ __forceinline__ float map_pi(float a) {   // MapToMinusPiToPi rex.py:26-41
+    const float TWO_PI = 6.283185307179586f;
+    float r = fmodf(a, TWO_PI);
+    if (r >= PI_F) r -= TWO_PI; else if (r < -PI_F) r += TWO_PI;
+    return r;
+}
+// _get_observation (+ RangeNormalize) for the env; lane 0 writes the 4 base terms, every lane its 3 angles (gallop)
+template <int TASK>
+__device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, const Lane& L, float* obs_row) {
+    float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
+    const float two_pi = 6.283185307179586f;
+    const float ub_ang = two_pi + 0.01f, ub_rate = (float)(2.0 * PI_D / P.cfg.sim_dt_d) + 0.01f;
+    float o[4] = {rpy[0], rpy[1], L.w.x, L.w.y};
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float v = o[j];
+        finite = finite && isfinite(v);
+        if (P.cfg.normalize) { float hi = (j < 2) ? ub_ang : ub_rate; v = 2.f * (v + hi) / (2.f * hi) - 1.f; }
+        o[j] = v;
+    }
+    if (leg == 0) { obs_row[0] = o[0]; obs_row[1] = o[1]; obs_row[2] = o[2]; obs_row[3] = o[3]; }
+    if (TASK == REXSIM_TASK_GALLOP) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float v = map_pi(L.q[j]);
+            finite = finite && isfinite(v);
+            if (P.cfg.normalize) v = 2.f * (v + ub_ang) / (2.f * ub_ang) - 1.f;
+            obs_row[4 + 3 * leg + j] = v;
+        }
+    }
+    return finite;
+}
+
+// -------------------------------------------------------------------------------------------------
+// the fused step kernel
+// -------------------------------------------------------------------------------------------------
+template <int TASK, int SIGNAL, int TERRAIN>
+__global__ void __launch_bounds__(128) step_kernel(const Params P) {
+    __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
+    __shared__ __align__(8) uint64_t bar;
+    tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
+
+    const int N = P.N;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int env = gid >> 2;
+    const int leg = gid & 3;
+    const bool valid = env < N;
+    if (!valid) env = N - 1;          // keep the warp converged for the shuffles; stores are masked
+    const RexSimConfig& c = P.cfg;
+    constexpr int A = (TASK == REXSIM_TASK_WALK) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 8)
+                    : (TASK == REXSIM_TASK_GALLOP) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 4)
+                    : (TASK == REXSIM_TASK_TURN) ? 2 : 1;
+    const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
+
+    Lane L; Task K;
+    load_lane(P.sf, P.si, N, env, leg, L);
+    load_task(P.sf, P.si, N, env, K);
+    float kp = P.sf[F_KP * (size_t)N + env], kd = P.sf[F_KD * (size_t)N + env];
+    int field = P.si[I_FIELD * (size_t)N + env];
+    float zoff = (TERRAIN == REXSIM_TERRAIN_RANDOM) ? P.field_zoff[field] : 0.f;
+
+    // action: ClipAction + RangeNormalize._denormalize_action (wrappers.py:218-236,262-265)
+    float act[A];
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        float v = P.actions[(size_t)env * A + j];
+        if (c.normalize) {
+            float b;
+            if (TASK == REXSIM_TASK_WALK) b = (SIGNAL == REXSIM_SIGNAL_IK) ? 0.4f : 0.01f;
+            else if (TASK == REXSIM_TASK_GALLOP) b = (SIGNAL == REXSIM_SIGNAL_IK) ? -0.4f : -0.3f;   // inverted Box: low=+b, high=-b
+            else if (TASK == REXSIM_TASK_TURN) b = 0.01f;
+            else b = 0.1f;
+            v = fminf(fmaxf(v, -1.f), 1.f);
+            v = (v + 1.f) / 2.f * (2.f * b) + (-b);
+        }
+        act[j] = v;
+    }
+    float cmd[3];
+    task_command<TASK, SIGNAL>(P, K, L, leg, act, cmd);
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) P.cmd_out[(size_t)(3 * leg + j) * N + env] = cmd[j];
+    }
+    // Rex.Step (rex.py:158-163)
+    for (int r = 0; r < c.action_repeat; r++) {
+        apply_action_and_step<TERRAIN>(P, sm, L, leg, cmd, kp, kd, field, zoff);
+        K.step_counter += 1;
+    }
+    // ---- reward (rex_gym_env.py:501-542; turn_env.py:362-367; standup_env.py:151-167) -----------------------
+    float reward;
+    M3 R = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
+    if (TASK == REXSIM_TASK_TURN) reward = 0.035f - fabsf(L.pos.x) - fabsf(L.pos.y);
+    else if (TASK == REXSIM_TASK_STANDUP) {
+        float pr = fabsf(L.pos.x) + fabsf(L.pos.y) + fabsf(0.21f - L.pos.z);
+        pr = (fabsf(pr) < 0.1f) ? 1.0f - pr : -pr;
+        if (L.pos.z > 0.21f) pr = -1.0f - pr;
+        reward = pr;
+    } else {
+        float cx = -L.pos.x;
+        if (K.flags & FL_BACKWARDS) cx = -cx;
+        K.target = fabsf(K.target);
+        float tp = K.target, fwd;
+        if (cx > tp + 0.15f) fwd = tp - cx;
+        else if (tp <= cx && cx <= tp + 0.15f) fwd = 1.0f;
+        else if (cx <= 0.05f) fwd = 0.0f;
+        else fwd = cx / tp;
+        float drift = -fabsf(L.pos.y);
+        float shake = -fabsf(R.c0.z + R.c1.z);          // rot_matrix[6] + rot_matrix[7]
+        float e = L.tau_obs[0] * L.qd[0] + L.tau_obs[1] * L.qd[1] + L.tau_obs[2] * L.qd[2];
+        float energy = -fabsf(sum4(e)) * (float)c.sim_dt_d;
+        reward = fwd * c.w_distance + energy * c.w_energy + drift * c.w_drift + shake * c.w_shake;
+    }
+    // ---- termination ----------------------------------------------------------------------------------------
+    bool done;
+    if (TASK == REXSIM_TASK_WALK || TASK == REXSIM_TASK_TURN) done = (R.c2.z < 0.85f) || (K.flags & FL_ENVGOAL);
+    else {
+        float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
+        bool fallen = fabsf(rpy[0]) > 0.3f || fabsf(rpy[1]) > 0.5f;
+        done = (TASK == REXSIM_TASK_STANDUP) ? fallen : (fallen || (K.flags & FL_ENVGOAL) || (L.pos.y > 0.3f));
+    }
+    K.env_step += 1;
+    if (c.max_episode_steps > 0 && K.env_step >= c.max_episode_steps) done = true;   // LimitDuration
+    // ---- non-finite guard (ConvertTo32Bit raises; here: flag + force done) ----------------------------------
+    bool finite = isfinite(reward) && isfinite(L.pos.x) && isfinite(L.pos.y) && isfinite(L.pos.z) &&
+                  isfinite(L.q[0]) && isfinite(L.q[1]) && isfinite(L.q[2]) && isfinite(L.qd[0]) && isfinite(L.qd[1]) && isfinite(L.qd[2]);
+    float* obs_row = P.obs + (size_t)env * O;
+    if (valid) finite = write_obs<TASK>(P, env, leg, L, obs_row) && finite;
+    finite = (sum4(finite ? 0.f : 1.f) == 0.f);
+    if (!finite) { L.err |= REXSIM_FLAG_NONFINITE; done = true; }
+    int err = L.err;
+    err |= __shfl_xor_sync(0xffffffffu, err, 1, 4); err |= __shfl_xor_sync(0xffffffffu, err, 2, 4);
+    if (valid && leg == 0) {
+        P.reward[env] = reward;
+        P.done[env] = done ? 1 : 0;
+        if (err) { P.err[env] |= err; atomicOr(&P.err[N], err); }
+    }
+    // ---- auto reset: done envs restart from the settled snapshot; obs = first observation of the new episode --
+    if (c.auto_reset && done) {
+        reset_from_snapshot(P, env, leg, L, K, kp, kd, field);
+        if (valid) write_obs<TASK>(P, env, leg, L, obs_row);
+    }
+    store_lane(P.sf, P.si, N, env, leg, L, K, valid);
+}
+
+// -------------------------------------------------------------------------------------------------
+// reset kernel: BatchEnv.reset(indices)
+// -------------------------------------------------------------------------------------------------
+template <int TASK>
+__global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_out) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = gid >> 2;
+    const int leg = gid & 3;
+    const int k = P.reset_idx ? P.reset_k : P.N;
+    const bool valid = j < k;
+    if (!valid) j = k - 1;
+    int env = P.reset_idx ? P.reset_idx[j] : j;
+    const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
+    Lane L; Task K; float kp, kd; int field;
+    reset_from_snapshot(P, env, leg, L, K, kp, kd, field);
+    if (valid && obs_out) write_obs<TASK>(P, env, leg, L, obs_out + (size_t)j * O);
+    store_lane(P.sf, P.si, P.N, env, leg, L, K, valid);
+}
+
+// -------------------------------------------------------------------------------------------------
+// settle kernel: Rex.Reset (rex.py:296-324) for one snapshot, 4 lanes: 100 sub-steps holding 'stand'
+// then reset_time/dt holding the task's init pose; writes the snapshot row
+// -------------------------------------------------------------------------------------------------
+template <int TERRAIN>
+__global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_f, int32_t* snap_i, int signal, int task) {
+    __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
+    __shared__ __align__(8) uint64_t bar;
+    tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
+    const int leg = threadIdx.x & 3;
+    const int field = P.settle_snapshot;
+    Lane L; Task K;
+    L.pos = mk(0.f, 0.f, 0.21f); L.qx = 0.f; L.qy = 0.f; L.qz = 0.f; L.qw = 1.f;
+    L.vl = mk(0, 0, 0); L.w = mk(0, 0, 0);
+    for (int j = 0; j < 3; j++) { L.q[j] = c_pose_stand[j]; L.qd[j] = 0.f; L.tau_obs[j] = 0.f; }
+    L.ovh = 0u; L.enabled = 7u; L.contact = 0; L.err = 0;
+    K.step_counter = 0; K.env_step = 0; K.flags = 0; K.end_step = 0; K.target = 0; K.torient = 0; K.iorient = 0;
+    K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
+    float zoff = (TERRAIN == REXSIM_TERRAIN_RANDOM) ? P.field_zoff[field] : 0.f;
+    float stand[3] = {c_pose_stand[0], c_pose_stand[1], c_pose_stand[2]};
+    float ip[3];
+    if (task == REXSIM_TASK_STANDUP) { ip[0] = (leg & 1) ? 0.4f : -0.4f; ip[1] = -1.5f; ip[2] = 6.f; }
+    else init_pose(signal, leg, ip);
+    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, field, zoff);
+    const int n2 = (int)(0.5 / P.cfg.sim_dt_d);
+    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, field, zoff);
+    {
+        float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
+        // snapshot rows are [NF] / [NI] with N = 1; the 8 replicas computed the same thing, the first one stores
+        store_lane(qf, qi, 1, 0, leg, L, K, threadIdx.x < 4);
+        int err = L.err;
+        err |= __shfl_xor_sync(0xffffffffu, err, 1, 4); err |= __shfl_xor_sync(0xffffffffu, err, 2, 4);
+        if (threadIdx.x == 0) {
+            qf[F_KP] = P.cfg.motor_kp; qf[F_KD] = P.cfg.motor_kd; qf[F_TORIENT] = 0.f; qf[F_IORIENT] = 0.f;
+            qi[I_RESETCNT] = 0; qi[I_FIELD] = field;
+            if (err) { P.err[0] |= err; atomicOr(&P.err[P.N], err); }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// get / set physical state
+// -------------------------------------------------------------------------------------------------
+__global__ void get_state_kernel(const Params P, float* out_f, int32_t* out_i) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.N) return;
+    const size_t N = P.N;
+    for (int w = 0; w < 37; w++) out_f[w * N + env] = P.sf[w * N + env];
+    out_i[0 * N + env] = P.si[I_STEP * N + env];
+    out_i[1 * N + env] = P.si[I_ENVSTEP * N + env];
+    out_i[2 * N + env] = P.si[I_FLAGS * N + env];
+    out_i[3 * N + env] = P.si[I_CONTACT * N + env];
+}
+__global__ void set_state_kernel(const Params P, const float* in_f) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.N) return;
+    const size_t N = P.N;
+    for (int w = 0; w < 37; w++) P.sf[w * N + env] = in_f[w * N + env];
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side launchers (called from rexsim_capi.cu)
+// -------------------------------------------------------------------------------------------------
+template <int TASK, int SIGNAL>
+static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
+    int threads = 128;
+    int blocks = (P.N * 4 + threads - 1) / threads;
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE><<<blocks, threads, 0, st>>>(P);
+    else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM><<<blocks, threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_step(const Params& P, cudaStream_t st) {
+    const int t = P.cfg.task, s = P.cfg.signal;
+    if (t == REXSIM_TASK_WALK) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_WALK, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_WALK, REXSIM_SIGNAL_OL>(P, st);
+    if (t == REXSIM_TASK_GALLOP) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_GALLOP, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_GALLOP, REXSIM_SIGNAL_OL>(P, st);
+    if (t == REXSIM_TASK_TURN) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_TURN, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_TURN, REXSIM_SIGNAL_OL>(P, st);
+    return launch_step_ts<REXSIM_TASK_STANDUP, REXSIM_SIGNAL_OL>(P, st);
+}
+cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st) {
+    int k = P.reset_idx ? P.reset_k : P.N;
+    if (k <= 0) return cudaSuccess;
+    int threads = 128, blocks = (k * 4 + threads - 1) / threads;
+    if (P.cfg.task == REXSIM_TASK_GALLOP) reset_kernel<REXSIM_TASK_GALLOP><<<blocks, threads, 0, st>>>(P, obs_out);
+    else reset_kernel<REXSIM_TASK_WALK><<<blocks, threads, 0, st>>>(P, obs_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_settle(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st) {
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) settle_kernel<REXSIM_TERRAIN_PLANE><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    else settle_kernel<REXSIM_TERRAIN_RANDOM><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    return cudaGetLastError();
+}
+cudaError_t launch_get_state(const Params& P, float* out_f, int32_t* out_i, cudaStream_t st) {
+    get_state_kernel<<<(P.N + 127) / 128, 128, 0, st>>>(P, out_f, out_i);
+    return cudaGetLastError();
+}
+cudaError_t launch_set_state(const Params& P, const float* in_f, cudaStream_t st) {
+    set_state_kernel<<<(P.N + 127) / 128, 128, 0, st>>>(P, in_f);
+    return cudaGetLastError();
+}
+
+}  // namespace rexsim

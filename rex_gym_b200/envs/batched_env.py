@@ -1,0 +1,334 @@
+"""BatchedRexEnv -- host-side mirror of the reference's env/BatchEnv surface over the CUDA library.
+
+Reference interface mirrored (same names, argument meaning, error behaviour):
+  * BatchEnv.step / reset / __len__ / __getitem__ / close   rex_gym/agents/tools/batch_env.py:18-115
+  * RexWalkEnv / RexReactiveEnv / RexTurnEnv constructor kwargs rex_gym/envs/gym/walk_env.py:31-50,
+    gallop_env.py:43-63, turn_env.py:30-49 (+ num_envs, device, and the fused training wrappers)
+  * gym ids RexWalk-v0 ... rex_gym/playground/__init__.py:17-57 via make()
+One call = one kernel launch for all N environments; there is no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _capi
+from ..model_tables import pack_model_tables, TOE_MARGIN
+from ..terrain import make_random_fields
+from .spaces import Box
+
+TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3}
+SIGNALS = {"ik": 0, "ol": 1}
+TERRAINS = {"plane": 0, "random": 1}
+DEFAULT_URDF_VERSION = "default"
+OBSERVATION_EPS = 0.01          # rex_gym/envs/rex_gym_env.py:19
+ACTION_BOUND = {("walk", "ik"): 0.4, ("walk", "ol"): 0.01, ("gallop", "ik"): 0.4, ("gallop", "ol"): 0.3,
+                ("turn", "ik"): 0.01, ("turn", "ol"): 0.01, ("standup", "ol"): 0.1, ("standup", "ik"): 0.1}
+
+ERR_NONFINITE, ERR_JOINT_LIMIT, ERR_BODY_CONTACT = 1, 2, 4
+
+
+class _DevArray(object):
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+class _Info(object):
+    """Lazy stand-in for BatchEnv's `tuple(infos)`: info[i] == {'action': motor command of env i}."""
+
+    def __init__(self, env):
+        self._env, self._cmd = env, None
+
+    def __len__(self):
+        return len(self._env)
+
+    def __getitem__(self, i):
+        if self._cmd is None:
+            self._cmd = self._env.last_command().t().contiguous().cpu().numpy()
+        return {"action": self._cmd[i]}
+
+
+class _EnvView(object):
+    """What BatchEnv.__getitem__ returns: a handle on one environment of the batch."""
+
+    def __init__(self, batch, index):
+        self._b, self.index = batch, index
+        self.observation_space, self.action_space = batch.observation_space, batch.action_space
+
+    @property
+    def env_step_counter(self):
+        return int(self._b.get_state()["env_step_counter"][self.index])
+
+
+class BatchedRexEnv(object):
+    metadata = {"render.modes": ["rgb_array"], "video.frames_per_second": 66}
+
+    def __init__(self, task="walk", num_envs=1, device="cuda:0", debug=False, urdf_version=None,
+                 control_time_step=None, action_repeat=None, control_latency=0.0, pd_latency=0.0, on_rack=False,
+                 motor_kp=1.0, motor_kd=0.02, render=False, num_steps_to_log=2000, env_randomizer=None,
+                 log_path=None, target_position=None, backwards=None, target_orient=None, init_orient=None,
+                 energy_weight=None, signal_type="ik", terrain_type="plane", terrain_id=None, mark="base",
+                 normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
+                 motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None):
+        if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
+            raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
+        if task not in TASKS or signal_type not in SIGNALS:
+            raise ValueError("unknown task/signal_type %r/%r" % (task, signal_type))
+        if terrain_type not in TERRAINS:
+            raise ValueError("terrain_type %r: only 'plane' and 'random' are built (csv/png assets live in the "
+                             "pybullet_data pip package)" % terrain_type)
+        if render or on_rack:
+            raise ValueError("render / on_rack are GUI debugging modes of the reference; not part of the batched path")
+        if control_latency or pd_latency:
+            raise ValueError("sensor latency is not built (reference default 0)")
+        if env_randomizer:
+            raise ValueError("env_randomizer hooks are Python callbacks; use motor_kp_range / motor_kd_range")
+        if not torch.cuda.is_available():
+            raise RuntimeError("rex_gym_b200 needs a CUDA device: there is no CPU fallback")
+        self._L = _capi.load()
+        self.task, self.signal_type, self.terrain_type, self.mark = task, signal_type, terrain_type, mark
+        self.device = torch.device(device)
+        self.num_envs = int(num_envs)
+        self.num_motors = 12 if mark == "base" else 18
+        rep = action_repeat or (6 if task == "gallop" else 5)
+        cts = control_time_step or (0.006 if task == "gallop" else 0.005)
+        self.control_time_step, self._action_repeat = cts, rep
+        self._time_step = cts / rep
+        tables, toe_npts = pack_model_tables(mark if mark == "base" else "base")
+        c = _capi.RexSimConfig()
+        c.num_envs, c.task, c.signal, c.terrain = self.num_envs, TASKS[task], SIGNALS[signal_type], TERRAINS[terrain_type]
+        c.num_motors, c.action_repeat = self.num_motors, rep
+        c.solver_iterations = solver_iterations or int(300 / rep)                      # rex_gym_env.py:25,184
+        c.sim_dt, c.sim_dt_d = self._time_step, self._time_step
+        c.motor_kp, c.motor_kd = motor_kp, motor_kd
+        c.kp_lo, c.kp_hi = motor_kp_range or (motor_kp, motor_kp)
+        c.kd_lo, c.kd_hi = motor_kd_range or (motor_kd, motor_kd)
+        c.target_position = float("nan") if target_position is None else target_position
+        c.backwards = -1 if backwards is None else int(bool(backwards))
+        c.target_orient = float("nan") if target_orient is None else target_orient
+        c.init_orient = float("nan") if init_orient is None else init_orient
+        c.w_distance, c.w_drift, c.w_shake = 1.0, 2.0, 0.005                            # rex_gym_env.py:56-59
+        c.w_energy = energy_weight if energy_weight is not None else (0.005 if task == "gallop" else 0.0005)
+        c.normalize, c.max_episode_steps, c.auto_reset, c.seed = int(normalize), int(max_episode_steps), int(auto_reset), seed
+        self._fields = None
+        with torch.cuda.device(self.device):
+            if terrain_type == "random":
+                self._fields = torch.from_numpy(make_random_fields(num_fields)).to(self.device).contiguous()
+                c.nfields, c.fields = num_fields, self._fields.data_ptr()
+                c.friction = 0.5 * 0.5          # URDF link default 0.5 x createMultiBody default 0.5
+            else:
+                c.nfields, c.fields = 0, None
+                c.friction = 0.5 * 1.0          # x plane.urdf lateral_friction 1
+            c.residual_threshold, c.erp_contact, c.erp_joint = 1e-7, 0.08, 0.2
+            c.toe_npts, c.toe_margin = toe_npts, TOE_MARGIN
+            self._cfg = c
+            h = C.c_void_p()
+            tb = np.ascontiguousarray(tables)
+            _capi.check(self._L.rexsim_create(C.byref(c), tb.ctypes.data, tb.size, C.byref(h)))
+        self._h = h
+        self.obs_dim = self._L.rexsim_obs_dim(c.task, c.num_motors)
+        self.action_dim = self._L.rexsim_action_dim(c.task, c.signal)
+        N, O, A = self.num_envs, self.obs_dim, self.action_dim
+        dev = self.device
+        self._obs = torch.zeros((N, O), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros((N,), dtype=torch.float32, device=dev)
+        self._done = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        self._act = torch.zeros((N, A), dtype=torch.float32, device=dev)
+        self._h_act = torch.zeros((N, A), dtype=torch.float32).pin_memory()
+        self._h_obs = torch.zeros((N, O), dtype=torch.float32).pin_memory()
+        self._h_reward = torch.zeros((N,), dtype=torch.float32).pin_memory()
+        self._h_done = torch.zeros((N,), dtype=torch.uint8).pin_memory()
+        self._h_err = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        p = C.c_void_p()
+        _capi.check(self._L.rexsim_error_flags(self._h, C.byref(p)))
+        self._err = torch.as_tensor(_DevArray(p.value, (N + 1,), "<i4", self), device=dev)
+        _capi.check(self._L.rexsim_last_command(self._h, C.byref(p)))
+        self._cmd = torch.as_tensor(_DevArray(p.value, (12, N), "<f4", self), device=dev)
+        nf, ni = C.c_int32(), C.c_int32()
+        _capi.check(self._L.rexsim_state_words(C.byref(c), C.byref(nf), C.byref(ni)))
+        pf, pi = C.c_void_p(), C.c_void_p()
+        _capi.check(self._L.rexsim_state_buffers(self._h, C.byref(pf), C.byref(pi)))
+        self._state_f = torch.as_tensor(_DevArray(pf.value, (nf.value, N), "<f4", self), device=dev)
+        self._state_i = torch.as_tensor(_DevArray(pi.value, (ni.value, N), "<i4", self), device=dev)
+        # spaces: raw task spaces, or the wrapper-visible ones when the training wrappers are fused in
+        b = ACTION_BOUND[(task, signal_type)]
+        if normalize:
+            self.action_space = Box(-np.inf * np.ones(A, np.float32), np.inf * np.ones(A, np.float32))   # ClipAction wrappers.py:257-260
+            self.observation_space = Box(-np.ones(O, np.float32), np.ones(O, np.float32))                # RangeNormalize :204-209
+        else:
+            hi = np.full(A, b, np.float32)
+            self.action_space = Box(hi, -hi) if task == "gallop" else Box(-hi, hi)                       # gallop_env.py:128-130
+            ub = np.full(O, 2 * math.pi, np.float32)
+            ub[2:4] = 2 * math.pi / self._time_step
+            self.observation_space = Box(-(ub + OBSERVATION_EPS), ub + OBSERVATION_EPS)
+        self._closed = False
+
+    # ---- BatchEnv surface ------------------------------------------------------------------------
+    def __len__(self):
+        return self.num_envs
+
+    def __getitem__(self, index):
+        if not -self.num_envs <= index < self.num_envs:
+            raise IndexError(index)
+        return _EnvView(self, index % self.num_envs)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def step(self, action):
+        """BatchEnv.step (batch_env.py:63-90).  numpy in -> numpy out (host buffers, copies inside);
+        CUDA tensor in -> CUDA tensors out (no host traffic)."""
+        N, A = self.num_envs, self.action_dim
+        on_device = isinstance(action, torch.Tensor) and action.is_cuda
+        with torch.cuda.device(self.device):
+            if on_device:
+                if tuple(action.shape) != (N, A):
+                    raise ValueError("Invalid action shape %s, expected %s" % (tuple(action.shape), (N, A)))
+                act = action.to(torch.float32).contiguous()
+            else:
+                a = np.asarray(action, dtype=np.float32)
+                if a.shape != (N, A):
+                    raise ValueError("Invalid action shape %s, expected %s" % (a.shape, (N, A)))
+                if not np.isfinite(a).all():
+                    raise ValueError("Invalid action: non-finite values")
+                self._h_act.numpy()[...] = a
+                self._act.copy_(self._h_act, non_blocking=True)
+                act = self._act
+            _capi.check(self._L.rexsim_step(self._h, act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(),
+                                            self._done.data_ptr(), self._stream()))
+            if on_device:
+                return self._obs, self._reward, self._done.bool(), _Info(self)
+            self._h_obs.copy_(self._obs, non_blocking=True)
+            self._h_reward.copy_(self._reward, non_blocking=True)
+            self._h_done.copy_(self._done, non_blocking=True)
+            self._h_err.copy_(self._err[N:N + 1], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        if int(self._h_err[0]) & ERR_NONFINITE:
+            raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
+        return self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), self._h_done.numpy().astype(bool), _Info(self)
+
+    def reset(self, indices=None):
+        """BatchEnv.reset (batch_env.py:92-109): observations of the reset environments."""
+        with torch.cuda.device(self.device):
+            if indices is None:
+                k, idx_ptr = self.num_envs, None
+            else:
+                if isinstance(indices, torch.Tensor):
+                    idx = indices.to(device=self.device, dtype=torch.int32).contiguous()
+                else:
+                    ia = np.asarray(indices, dtype=np.int64).reshape(-1)
+                    if ia.size and (ia.min() < 0 or ia.max() >= self.num_envs):
+                        raise IndexError("reset index out of range")
+                    idx = torch.from_numpy(ia.astype(np.int32)).to(self.device)
+                k, idx_ptr = int(idx.numel()), idx.data_ptr()
+            out = torch.zeros((k, self.obs_dim), dtype=torch.float32, device=self.device)
+            if k > 0:
+                _capi.check(self._L.rexsim_reset(self._h, idx_ptr, k, out.data_ptr(), self._stream()))
+            if isinstance(indices, torch.Tensor):
+                return out
+            return out.cpu().numpy()
+
+    def close(self):
+        if not self._closed:
+            self._closed = True
+            torch.cuda.synchronize(self.device)
+            self._L.rexsim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- extras ------------------------------------------------------------------------------------
+    def get_state(self):
+        """Physical state of every env (pybullet getBasePositionAndOrientation/getBaseVelocity/getJointState)."""
+        N, nm = self.num_envs, 12
+        f = torch.zeros((13 + 2 * nm, N), dtype=torch.float32, device=self.device)
+        i = torch.zeros((4, N), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.rexsim_get_state(self._h, f.data_ptr(), i.data_ptr(), self._stream()))
+        f, i = f.cpu().numpy(), i.cpu().numpy()
+        return dict(pos=f[0:3].T.copy(), quat=f[3:7].T.copy(), linvel=f[7:10].T.copy(), angvel=f[10:13].T.copy(),
+                    q=f[13:13 + nm].T.copy(), qd=f[13 + nm:13 + 2 * nm].T.copy(),
+                    step_counter=i[0].copy(), env_step_counter=i[1].copy(), flags=i[2].copy(), contact_mask=i[3].copy())
+
+    def set_state(self, pos, quat, linvel, angvel, q, qd):
+        N, nm = self.num_envs, 12
+        f = np.concatenate([np.asarray(x, np.float32).reshape(N, -1).T for x in (pos, quat, linvel, angvel, q, qd)], axis=0)
+        t = torch.from_numpy(np.ascontiguousarray(f)).to(self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.rexsim_set_state(self._h, t.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def last_command(self):
+        """[12, N] motor commands of the last step (info['action'], rex_gym_env.py:414)."""
+        return self._cmd
+
+    def error_flags(self):
+        return self._err[:self.num_envs]
+
+    def check_errors(self):
+        e = int(self._err[self.num_envs].item())
+        if e & ERR_NONFINITE:
+            raise ValueError("Infinite observation encountered.")
+        return e
+
+    def state_dict(self):
+        """Exact checkpoint of the whole batch (the reference never checkpoints env state)."""
+        return {"state_f": self._state_f.clone(), "state_i": self._state_i.clone()}
+
+    def load_state_dict(self, sd):
+        self._state_f.copy_(sd["state_f"])
+        self._state_i.copy_(sd["state_i"])
+
+    @property
+    def launch_count(self):
+        return int(self._L.rexsim_launch_count(self._h))
+
+    def seed(self, seed=None):
+        return [seed]
+
+    def render(self, mode="rgb_array", close=False):
+        return np.array([])
+
+
+class RexWalkBatchEnv(BatchedRexEnv):
+    """rex_gym/envs/gym/walk_env.py:16 RexWalkEnv, batched."""
+
+    def __init__(self, num_envs=1, **kw):
+        kw.setdefault("control_time_step", 0.005); kw.setdefault("action_repeat", 5)
+        super().__init__(task="walk", num_envs=num_envs, **kw)
+
+
+class RexGallopBatchEnv(BatchedRexEnv):
+    """rex_gym/envs/gym/gallop_env.py:28 RexReactiveEnv, batched."""
+
+    def __init__(self, num_envs=1, **kw):
+        kw.setdefault("control_time_step", 0.006); kw.setdefault("action_repeat", 6)
+        kw.setdefault("energy_weight", 0.005)
+        super().__init__(task="gallop", num_envs=num_envs, **kw)
+
+
+class RexTurnBatchEnv(BatchedRexEnv):
+    """rex_gym/envs/gym/turn_env.py:20 RexTurnEnv, batched."""
+
+    def __init__(self, num_envs=1, **kw):
+        kw.setdefault("control_time_step", 0.005); kw.setdefault("action_repeat", 5)
+        super().__init__(task="turn", num_envs=num_envs, **kw)
+
+
+# gym ids of rex_gym/playground/__init__.py:17-57 -> batched classes
+ENV_IDS = {"RexWalk-v0": RexWalkBatchEnv, "RexGalloping-v0": RexGallopBatchEnv, "RexTurn-v0": RexTurnBatchEnv}
+
+
+def make(env_id, num_envs=1, **kwargs):
+    """gym.make(id, **args) equivalent (rex_gym/playground/trainer.py:47) returning a whole batch."""
+    if env_id not in ENV_IDS:
+        raise ValueError("env id %r not built (have %s)" % (env_id, sorted(ENV_IDS)))
+    return ENV_IDS[env_id](num_envs=num_envs, **kwargs)
