@@ -65,8 +65,19 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.oracle import OracleSim
-    cores = os.cpu_count() or 1
-    n = 256
+    try:
+        cores = len(os.sched_getaffinity(0))        # cores this process may actually use (cgroup/affinity aware)
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:                                            # a cgroup CPU quota below the affinity count would oversubscribe
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            cores = min(cores, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    cores = max(1, min(cores, 64))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    n = 32 * cores                                  # 32 envs per thread per step keeps the fork/join overhead small
     sim = OracleSim(n, "walk", "ik", target_position=2.0, backwards=False, normalize=True, max_episode_steps=2000)
     sim.reset()
     rng = np.random.default_rng(1234)
@@ -88,7 +99,7 @@ def run_reference(args):
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "walk-ik flat, 256-env sample per step, fp64 CPU port of the path"},
+                      "config": {"workload": f"walk-ik flat, {n}-env sample per step, fp64 CPU port of the path on {cores} threads"},
                       "cpu_baseline": cb,
                       "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -87,6 +87,7 @@ typedef struct {
     float erp_contact, erp_joint;
     int32_t toe_npts;                 /* valid points per toe in the model table */
     float toe_margin;
+    int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */
 } RexSimConfig;
 
 typedef struct RexSim RexSim;
@@ -120,6 +121,9 @@ int rexsim_error_flags(RexSim* sim, int32_t** err_flags);
 int rexsim_last_command(RexSim* sim, float** cmd);
 /* kernels launched by this handle since create (the bench reports it) */
 int64_t rexsim_launch_count(const RexSim* sim);
+/* the counter-based generator behind every reset draw (replaces Python's unseeded `random`,
+ * walk_env.py:133-147, gallop_env.py:151, turn_env.py:138,147); host-callable so tests can pin it */
+uint32_t rexsim_rand_u32(uint64_t seed, uint32_t global_env, uint32_t reset_count, uint32_t slot);
 const char* rexsim_last_error(void);
 
 #ifdef __cplusplus

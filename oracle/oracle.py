@@ -46,7 +46,7 @@ class RexoConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("seed", C.c_uint64),
         ("nfields", C.c_int32), ("fields", C.POINTER(C.c_float)), ("friction", C.c_double),
         ("residual_threshold", C.c_double), ("erp_contact", C.c_double), ("erp_joint", C.c_double),
-        ("settle_on_reset", C.c_int32),
+        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32),
     ]
 
 
@@ -182,7 +182,7 @@ class OracleSim:
                  kp_range=None, kd_range=None, target_position=None, backwards=None,
                  target_orient=None, init_orient=None, energy_weight=None, normalize=False,
                  max_episode_steps=0, seed=1234, nfields=0, fields=None, toes_only=False, settle=True,
-                 solver_iterations=None, residual_threshold=1e-7):
+                 solver_iterations=None, residual_threshold=1e-7, env_offset=0):
         self.L = lib(f32)
         self.model, self.model_json = load_model(mark, toes_only=toes_only)
         c = RexoConfig()
@@ -194,8 +194,9 @@ class OracleSim:
         c.sim_dt = cts / rep
         c.solver_iterations = solver_iterations or int(300 / rep)
         c.motor_kp, c.motor_kd = motor_kp, motor_kd
-        c.kp_lo, c.kp_hi = kp_range or (motor_kp, motor_kp)
-        c.kd_lo, c.kd_hi = kd_range or (motor_kd, motor_kd)
+        # randomisation bounds travel through the C ABI as float32: round them the same way here
+        c.kp_lo, c.kp_hi = [float(np.float32(x)) for x in kp_range] if kp_range else (motor_kp, motor_kp)
+        c.kd_lo, c.kd_hi = [float(np.float32(x)) for x in kd_range] if kd_range else (motor_kd, motor_kd)
         c.target_position = float("nan") if target_position is None else target_position
         c.backwards = -1 if backwards is None else int(bool(backwards))
         c.target_orient = float("nan") if target_orient is None else target_orient
@@ -215,6 +216,7 @@ class OracleSim:
         c.residual_threshold = residual_threshold
         c.erp_contact, c.erp_joint = 0.08, 0.2
         c.settle_on_reset = int(settle)
+        c.env_offset = int(env_offset)
         self.cfg = c
         self.h = self.L.rexo_create(C.byref(self.model), C.byref(c))
         self.N = num_envs

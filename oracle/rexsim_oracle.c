@@ -197,7 +197,7 @@ uint32_t rexo_rand_u32(uint64_t seed, uint32_t env, uint32_t reset_count, uint32
     return (uint32_t)(z >> 32);
 }
 static double rand_uniform(const RexoSim* s, int env, uint32_t rc, uint32_t slot, double a, double b) {
-    double u = (double)(rexo_rand_u32(s->c.seed, (uint32_t)env, rc, slot) >> 8) * (1.0 / 16777216.0);
+    double u = (double)(rexo_rand_u32(s->c.seed, (uint32_t)env + (uint32_t)s->c.env_offset, rc, slot) >> 8) * (1.0 / 16777216.0);
     return a + (b - a) * u;   /* random.uniform(a,b) = a + (b-a)*random() */
 }
 
@@ -931,10 +931,13 @@ static void reset_env(RexoSim* s, int i) {
     RexoEnv* e = &s->env[i];
     const RexoConfig* c = &s->c;
     uint32_t rc = e->reset_count + 1;
-    int field = (c->terrain == REXO_TERRAIN_RANDOM) ? (int)((i + rc) % (uint32_t)c->nfields) : 0;
+    int field = (c->terrain == REXO_TERRAIN_RANDOM) ? (int)(((uint32_t)i + (uint32_t)c->env_offset + rc) % (uint32_t)c->nfields) : 0;
     RexoEnv* snap = &s->snapshot[field];
     double kp = c->kp_lo == c->kp_hi ? c->motor_kp : rand_uniform(s, i, rc, 4, c->kp_lo, c->kp_hi);
     double kd = c->kd_lo == c->kd_hi ? c->motor_kd : rand_uniform(s, i, rc, 5, c->kd_lo, c->kd_hi);
+    /* the C ABI carries gains as float32: drawn gains are rounded the same way so they compare bit-exactly */
+    if (c->kp_lo != c->kp_hi) kp = (double)(float)kp;
+    if (c->kd_lo != c->kd_hi) kd = (double)(float)kd;
     /* the settle (rex.py:314-323) runs with the nominal gains; per-env randomised gains (ours, the
      * reference ships no randomizer) apply from the first control step on, so the settled state only
      * depends on (init pose, field) and is computed once per field */
@@ -950,7 +953,7 @@ static void reset_env(RexoSim* s, int i) {
     e->backwards = 0; e->clockwise = 0; e->end_time = 0;
     e->target_position = 0; e->target_orient = 0; e->init_orient = 0;
     if (c->task == REXO_TASK_WALK) {   /* walk_env.py:125-154 */
-        if (c->backwards < 0) e->backwards = (rexo_rand_u32(c->seed, i, rc, 0) >> 31) ? 1 : 0;
+        if (c->backwards < 0) e->backwards = (rexo_rand_u32(c->seed, (uint32_t)i + (uint32_t)c->env_offset, rc, 0) >> 31) ? 1 : 0;
         else e->backwards = c->backwards;
         if (isnan(c->target_position)) {
             double bound = e->backwards ? -3 : 3, half = e->backwards ? -2 : 1;   /* bound//2 floor-div */

@@ -21,13 +21,13 @@ class RexSimConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("seed", C.c_uint64), ("nfields", C.c_int32), ("fields", C.c_void_p),
         ("friction", C.c_float), ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
-        ("toe_npts", C.c_int32), ("toe_margin", C.c_float),
+        ("toe_npts", C.c_int32), ("toe_margin", C.c_float), ("env_offset", C.c_int32),
     ]
 
 
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
            "rexsim_step", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
-           "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error"]
+           "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
 
 _LIB = None
 
@@ -60,6 +60,8 @@ def load():
     L.rexsim_launch_count.argtypes = [C.c_void_p]
     L.rexsim_launch_count.restype = C.c_int64
     L.rexsim_last_error.restype = C.c_char_p
+    L.rexsim_rand_u32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rexsim_rand_u32.restype = C.c_uint32
     _LIB = L
     return L
 

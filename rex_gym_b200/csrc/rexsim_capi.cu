@@ -181,5 +181,8 @@ int rexsim_last_command(RexSim* s, float** cmd) {
     return REXSIM_OK;
 }
 int64_t rexsim_launch_count(const RexSim* s) { return s ? s->launches : 0; }
+uint32_t rexsim_rand_u32(uint64_t seed, uint32_t global_env, uint32_t reset_count, uint32_t slot) {
+    return rand_u32(seed, global_env, reset_count, slot);
+}
 
 }  // extern "C"

@@ -775,7 +775,8 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
     const RexSimConfig& c = P.cfg;
     const int N = P.N;
     uint32_t rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env] + 1u;
-    field = (c.terrain == REXSIM_TERRAIN_RANDOM) ? (int)(((uint32_t)env + rc) % (uint32_t)c.nfields) : 0;
+    const uint32_t genv = (uint32_t)env + (uint32_t)c.env_offset;   // global env id: draws do not depend on the sharding
+    field = (c.terrain == REXSIM_TERRAIN_RANDOM) ? (int)((genv + rc) % (uint32_t)c.nfields) : 0;
     const float* sf = P.snap_f + (size_t)field * NF;
     const int32_t* si = P.snap_i + (size_t)field * NI;
     load_lane(sf, si, 1, 0, leg, L);
@@ -784,18 +785,18 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
     K.flags = K.flags & ~((1 << FL_ENABLED_SHIFT) - 1);
     K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
     K.target = 0.f; K.torient = 0.f; K.iorient = 0.f;
-    kp = (c.kp_lo == c.kp_hi) ? c.motor_kp : (float)rand_uniform(c.seed, env, rc, 4, c.kp_lo, c.kp_hi);
-    kd = (c.kd_lo == c.kd_hi) ? c.motor_kd : (float)rand_uniform(c.seed, env, rc, 5, c.kd_lo, c.kd_hi);
+    kp = (c.kp_lo == c.kp_hi) ? c.motor_kp : (float)rand_uniform(c.seed, genv, rc,4, c.kp_lo, c.kp_hi);
+    kd = (c.kd_lo == c.kd_hi) ? c.motor_kd : (float)rand_uniform(c.seed, genv, rc,5, c.kd_lo, c.kd_hi);
     if (c.task == REXSIM_TASK_WALK) {
-        int bw = (c.backwards < 0) ? (int)(rand_u32(c.seed, env, rc, 0) >> 31) : c.backwards;
+        int bw = (c.backwards < 0) ? (int)(rand_u32(c.seed, genv, rc,0) >> 31) : c.backwards;
         if (bw) K.flags |= FL_BACKWARDS;
-        if (isnan(c.target_position)) K.target = (float)rand_uniform(c.seed, env, rc, 1, bw ? -2.0 : 1.0, bw ? -3.0 : 3.0);
+        if (isnan(c.target_position)) K.target = (float)rand_uniform(c.seed, genv, rc,1, bw ? -2.0 : 1.0, bw ? -3.0 : 3.0);
         else K.target = c.target_position;
     } else if (c.task == REXSIM_TASK_GALLOP) {
-        K.target = isnan(c.target_position) ? (float)rand_uniform(c.seed, env, rc, 1, 1.0, 3.0) : c.target_position;
+        K.target = isnan(c.target_position) ? (float)rand_uniform(c.seed, genv, rc,1, 1.0, 3.0) : c.target_position;
     } else if (c.task == REXSIM_TASK_TURN) {
-        double to = isnan(c.target_orient) ? rand_uniform(c.seed, env, rc, 2, 0.2, 6.0) : (double)c.target_orient;
-        double io = isnan(c.init_orient) ? rand_uniform(c.seed, env, rc, 3, 0.2, 6.0) : (double)c.init_orient;
+        double to = isnan(c.target_orient) ? rand_uniform(c.seed, genv, rc,2, 0.2, 6.0) : (double)c.target_orient;
+        double io = isnan(c.init_orient) ? rand_uniform(c.seed, genv, rc,3, 0.2, 6.0) : (double)c.init_orient;
         K.torient = (float)to; K.iorient = (float)io;
         double diff = fabs(io - to);
         bool cw = false;

@@ -73,7 +73,7 @@ class BatchedRexEnv(object):
                  log_path=None, target_position=None, backwards=None, target_orient=None, init_orient=None,
                  energy_weight=None, signal_type="ik", terrain_type="plane", terrain_id=None, mark="base",
                  normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
-                 motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None):
+                 motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0):
         if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
             raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
         if task not in TASKS or signal_type not in SIGNALS:
@@ -125,6 +125,7 @@ class BatchedRexEnv(object):
                 c.friction = 0.5 * 1.0          # x plane.urdf lateral_friction 1
             c.residual_threshold, c.erp_contact, c.erp_joint = 1e-7, 0.08, 0.2
             c.toe_npts, c.toe_margin = toe_npts, TOE_MARGIN
+            c.env_offset = int(env_offset)
             self._cfg = c
             h = C.c_void_p()
             tb = np.ascontiguousarray(tables)

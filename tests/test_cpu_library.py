@@ -1,0 +1,110 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/rexsim.h declares (no compute calls
+without a GPU), host-only entry points, packer layout, no-CPU-fallback behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "rexsim.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rexsim_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rex_gym_b200 import _capi
+    L = _capi.load()
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_capi.EXPORTS) == names
+
+
+def test_host_only_entry_points():
+    from rex_gym_b200 import _capi
+    L = _capi.load()
+    # widths of the reference spaces: walk_env.py:108-113, gallop_env.py:123-127,349-356, turn_env.py:104-108
+    assert [L.rexsim_action_dim(t, s) for t, s in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 1))] == [2, 8, 2, 4, 2, 2, 1]
+    assert [L.rexsim_obs_dim(t, 12) for t in range(4)] == [4, 16, 4, 4]
+    cfg = _capi.RexSimConfig()
+    nf, ni = C.c_int32(), C.c_int32()
+    assert L.rexsim_state_words(C.byref(cfg), C.byref(nf), C.byref(ni)) == 0
+    assert nf.value == 43 and ni.value == 14
+
+
+def test_create_rejects_bad_arguments_without_touching_the_gpu():
+    from rex_gym_b200 import _capi
+    L = _capi.load()
+    cfg = _capi.RexSimConfig()
+    h = C.c_void_p()
+    tb = np.zeros(952, np.float32)
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 951, C.byref(h)) == -2          # model size
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -1          # num_envs = 0
+    cfg.num_envs, cfg.num_motors, cfg.task = 8, 18, 0
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -4          # arm not built
+    assert b"arm" in L.rexsim_last_error()
+    with pytest.raises(ValueError):
+        _capi.check(-4)
+
+
+def test_rng_is_bit_identical_to_the_oracle():
+    from rex_gym_b200 import _capi
+    from oracle import oracle as O
+    L, R = _capi.load(), O.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        s, e, r, k = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**31)), int(rng.integers(0, 2**31)), int(rng.integers(0, 8))
+        assert L.rexsim_rand_u32(s, e, r, k) == R.rexo_rand_u32(s, e, r, k)
+
+
+def test_model_table_packer_layout():
+    from rex_gym_b200.model_tables import pack_model_tables, MT_LEG, MT_TOE, MT_BOX, MT_BASEBOX, MT_FLOATS
+    t, npts = pack_model_tables("base")
+    assert t.dtype == np.float32 and t.shape == (MT_FLOATS,) and MT_FLOATS * 4 % 16 == 0   # TMA bulk copy granularity
+    assert npts == 27
+    assert abs(t[0] - 1.3) < 1e-6 and abs(t[10] - 1.2) < 1e-6                             # merged base / un-merged root mass
+    legs = t[MT_LEG:MT_LEG + 192].reshape(4, 3, 16)
+    np.testing.assert_allclose(legs[:, 0, :3], [[-0.093, -0.036, 0], [-0.093, 0.036, 0], [0.093, -0.036, 0], [0.093, 0.036, 0]], atol=1e-7)
+    np.testing.assert_allclose(legs[:, 1, 3], 0.6, atol=1e-6)                            # leg link + 0.5 kg cover (rex.urdf)
+    np.testing.assert_allclose(legs[:, 2, 7], -0.1, atol=1e-6); np.testing.assert_allclose(legs[:, 2, 14], 2.59, atol=1e-6)
+    toe = t[MT_TOE:MT_TOE + 384].reshape(4, 32, 3)
+    assert np.all(toe[:, npts:] == 0) and np.all(np.abs(toe[:, :npts]).max(axis=(1, 2)) < 0.16)
+    assert t[MT_BOX:MT_BASEBOX].reshape(4, 3, 8, 3).shape == (4, 3, 8, 3)
+
+
+def test_no_cpu_fallback():
+    import torch
+    import rex_gym_b200 as R
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        R.make("RexWalk-v0", num_envs=4)
+
+
+def test_reference_surface_names():
+    import rex_gym_b200 as R
+    assert set(R.ENV_IDS) == {"RexWalk-v0", "RexGalloping-v0", "RexTurn-v0"}       # playground/__init__.py:17-57
+    for m in ("step", "reset", "close", "__len__", "__getitem__"):                  # batch_env.py:44-115
+        assert hasattr(R.BatchedRexEnv, m)
+    with pytest.raises(ValueError):
+        R.make("RexGo-v0")
+
+
+def test_terrain_bank_follows_the_reference_stream():
+    """field 0 = first generate_terrain() of the reference: random.seed(10), 2x2 blocks of U(0, 0.05)
+    (rex_gym/model/terrain.py:26,36-44)."""
+    import random
+    from rex_gym_b200.terrain import make_random_fields
+    f = make_random_fields(2)
+    rnd = random.Random(10)
+    first = [rnd.uniform(0, 0.05) for _ in range(5)]
+    assert f.shape == (2, 256, 256)
+    np.testing.assert_allclose(f[0].reshape(-1)[[0, 1, 256, 257]], np.float32(first[0]))
+    np.testing.assert_allclose(f[0].reshape(-1)[2], np.float32(first[1]))
+    assert f.min() >= 0 and f.max() <= 0.05 and not np.array_equal(f[0], f[1])

