@@ -49,8 +49,8 @@ enum { REXSIM_TERRAIN_PLANE = 0, REXSIM_TERRAIN_RANDOM = 1 };
 /* per-env device error bits (rexsim_step ORs them into err_flags[env]) */
 enum {
     REXSIM_FLAG_NONFINITE = 1,        /* non-finite state/obs/reward (ConvertTo32Bit raises, wrappers.py:522,542) */
-    REXSIM_FLAG_JOINT_LIMIT = 2,      /* a joint crossed its URDF limit: needs the joint-limit rows */
-    REXSIM_FLAG_BODY_CONTACT = 4,     /* a non-toe collision box reached the ground: needs the body rows */
+    REXSIM_FLAG_JOINT_LIMIT = 2,      /* more than one joint limit violated in one leg: only one limit row per leg is modelled */
+    REXSIM_FLAG_BODY_CONTACT = 4,     /* reserved (body contacts are solved since the generic row path exists) */
 };
 
 #define REXSIM_MAX_TOE_PTS 32
@@ -110,7 +110,8 @@ int rexsim_reset(RexSim* sim, const int32_t* idx, int32_t k, float* obs_out, voi
 
 /* Physical state of every env, SoA on device: out_f dev [13 + 2*nm][N] =
  *   pos[3], quat[4] (x,y,z,w), linvel[3], angvel[3], q[nm], qd[nm];  out_i dev [4][N] =
- *   step_counter, env_step_counter, flags, last-substep contact mask (bit l: toe l) */
+ *   step_counter, env_step_counter, flags, last-substep contact mask (bit 0: base group, bit 1+2l: shoulder/leg
+ *   boxes of leg l, bit 2+2l: foot box + toe hull of leg l) */
 int rexsim_get_state(RexSim* sim, float* out_f, int32_t* out_i, void* stream);
 int rexsim_set_state(RexSim* sim, const float* in_f, void* stream);
 /* raw SoA state for checkpoint/resume: [n_float][N] f32 and [n_int][N] i32 device buffers */

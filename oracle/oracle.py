@@ -27,9 +27,9 @@ class RexoModel(C.Structure):
         ("lower", C.c_double * MAXB), ("upper", C.c_double * MAXB), ("mass", C.c_double * MAXB),
         ("com", (C.c_double * 3) * MAXB), ("inertia", (C.c_double * 9) * MAXB),
         ("root_mass", C.c_double), ("root_inertia", C.c_double * 3),
-        ("nshape", C.c_int32), ("shape_body", C.c_int32 * MAXSHAPE), ("shape_start", C.c_int32 * MAXSHAPE),
-        ("shape_npts", C.c_int32 * MAXSHAPE), ("shape_margin", C.c_double * MAXSHAPE),
-        ("shape_enabled", C.c_int32 * MAXSHAPE), ("pts", (C.c_double * 3) * MAXPTS),
+        ("nshape", C.c_int32), ("shape_start", C.c_int32 * MAXSHAPE), ("shape_npts", C.c_int32 * MAXSHAPE),
+        ("shape_enabled", C.c_int32 * MAXSHAPE), ("pt_body", C.c_int32 * MAXPTS), ("pt_margin", C.c_double * MAXPTS),
+        ("pts", (C.c_double * 3) * MAXPTS),
         ("nmotor", C.c_int32), ("motor_dof", C.c_int32 * MAXDOF),
     ]
 
@@ -122,7 +122,6 @@ def load_model(mark="base", toes_only=False):
     m = RexoModel()
     bodies = j["bodies"]
     m.nb, m.ndof = len(bodies), len(bodies) - 1
-    npts = nshape = 0
     for i, b in enumerate(bodies):
         m.parent[i] = b["parent"]
         R = _rpy_to_mat(b.get("joint_rpy", [0, 0, 0]))
@@ -135,19 +134,26 @@ def load_model(mark="base", toes_only=False):
             m.inertia[i][a] = np.asarray(b["inertia"]).flat[a]
         m.lower[i], m.upper[i] = b.get("lower", 0.0), b.get("upper", 0.0)
         m.mass[i] = b["mass"]
-        for sh in b["shapes"]:
-            m.shape_body[nshape] = i
-            m.shape_start[nshape] = npts
-            m.shape_npts[nshape] = len(sh["points"])
-            is_toe = sh["kind"] == "hull"
-            m.shape_margin[nshape] = TOE_MARGIN if is_toe else 0.0
-            m.shape_enabled[nshape] = 1 if (is_toe or not toes_only) else 0
-            for p in sh["points"]:
-                for a in range(3):
-                    m.pts[npts][a] = p[a]
-                npts += 1
-            nshape += 1
-    m.nshape = nshape
+    # contact groups (one contact per group): base; per leg {shoulder+leg boxes}, {foot box + toe hull}; arm bodies
+    groups = [[0]] + [g for l in range(4) for g in ([1 + 3 * l, 2 + 3 * l], [3 + 3 * l])] + [[i] for i in range(13, len(bodies))]
+    npts = 0
+    for gi, gb in enumerate(groups):
+        m.shape_start[gi] = npts
+        is_foot = gi >= 1 and gi <= 8 and gi % 2 == 0
+        m.shape_enabled[gi] = 1 if (is_foot or not toes_only) else 0
+        for bi in gb:
+            for sh in bodies[bi]["shapes"]:
+                is_toe = sh["kind"] == "hull"
+                if toes_only and not is_toe:
+                    continue
+                for p in sh["points"]:
+                    for a in range(3):
+                        m.pts[npts][a] = p[a]
+                    m.pt_body[npts] = bi
+                    m.pt_margin[npts] = TOE_MARGIN if is_toe else 0.0
+                    npts += 1
+        m.shape_npts[gi] = npts - m.shape_start[gi]
+    m.nshape = len(groups)
     m.root_mass = j["root_mass"]
     for a in range(3):
         m.root_inertia[a] = j["root_inertia"][a]

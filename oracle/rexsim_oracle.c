@@ -558,19 +558,21 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
     e->limit_rows = nlim;
     e->contact_mask = 0;
     const real breaking = 0.0005, slop = 1e-5;
-    for (int sh = 0; sh < m->nshape; sh++) {    /* deepest sample point of each shape vs ground */
+    for (int sh = 0; sh < m->nshape; sh++) {    /* deepest sample point of each contact group vs ground */
         e->contact_vertex[sh] = -1;
         if (!m->shape_enabled[sh]) continue;
-        int b = m->shape_body[sh];
+        int b = 0;
         real best = 1e30, bp[3] = {0, 0, 0}, bn[3] = {0, 0, 1}; int bi = -1;
         for (int v = 0; v < m->shape_npts[sh]; v++) {
-            const double* pl = m->pts[m->shape_start[sh] + v];
+            const int pi = m->shape_start[sh] + v;
+            const int pb = m->pt_body[pi];
+            const double* pl = m->pts[pi];
             real lp[3] = {pl[0], pl[1], pl[2]}, wp[3], n[3], d;
-            m3v(k->Rw[b], lp, wp);
-            for (int a = 0; a < 3; a++) wp[a] += k->pw[b][a];
+            m3v(k->Rw[pb], lp, wp);
+            for (int a = 0; a < 3; a++) wp[a] += k->pw[pb][a];
             ground_query(s, e, wp, &d, n);
-            d -= m->shape_margin[sh];
-            if (d < best) { best = d; bi = v; for (int a = 0; a < 3; a++) { bp[a] = wp[a]; bn[a] = n[a]; } }
+            d -= m->pt_margin[pi];
+            if (d < best) { best = d; bi = v; b = pb; for (int a = 0; a < 3; a++) { bp[a] = wp[a]; bn[a] = n[a]; } }
         }
         if (bi < 0 || best > breaking) continue;
         e->contact_mask |= (1 << sh);

@@ -33,7 +33,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(HERE, "librexsim.so")
+    # REXSIM_LIB: developer override to A/B kernels built with other flags (must still be an in-tree build)
+    return os.environ.get("REXSIM_LIB") or os.path.join(HERE, "librexsim.so")
 
 
 def load():
@@ -41,7 +42,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if _build.needs_build():
+    if not os.environ.get("REXSIM_LIB") and _build.needs_build():
         _build.build()
     L = C.CDLL(lib_path())
     L.rexsim_obs_dim.argtypes = [C.c_int32, C.c_int32]

@@ -61,7 +61,6 @@ static int validate(const RexSimConfig* c) {
     if (c->num_envs <= 0) return fail(REXSIM_ERR_INVALID, "num_envs must be positive");
     if (c->task < 0 || c->task > 3 || c->signal < 0 || c->signal > 1) return fail(REXSIM_ERR_INVALID, "bad task/signal");
     if (c->num_motors != 12) return fail(REXSIM_ERR_UNSUPPORTED, "mark='arm' (18 motors) is not built yet");
-    if (c->task == REXSIM_TASK_STANDUP) return fail(REXSIM_ERR_UNSUPPORTED, "standup needs the joint-limit/body-contact rows (not built yet)");
     if (c->action_repeat <= 0 || c->solver_iterations <= 0 || !(c->sim_dt_d > 0)) return fail(REXSIM_ERR_INVALID, "bad time stepping");
     if (c->terrain == REXSIM_TERRAIN_RANDOM && (c->nfields <= 0 || !c->fields)) return fail(REXSIM_ERR_INVALID, "random terrain needs a heightfield bank");
     if (c->terrain != REXSIM_TERRAIN_PLANE && c->terrain != REXSIM_TERRAIN_RANDOM) return fail(REXSIM_ERR_UNSUPPORTED, "terrain type");

@@ -4,6 +4,10 @@
 
 namespace rexsim {
 
+// resident CTAs per SM the step kernel is compiled for (register cap = 65536 / (128 * REXSIM_MIN_BLOCKS))
+#ifndef REXSIM_MIN_BLOCKS
+#define REXSIM_MIN_BLOCKS 1
+#endif
 #define PI_F 3.14159265358979323846f
 #define PI_D 3.14159265358979323846
 
@@ -170,6 +174,10 @@ __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {   // btPlaneSp
     }
 }
 
+// generic-path Gauss-Seidel order after the 4 limit rows: normals (base, then per leg upper, foot), then frictions
+__constant__ int c_seq_owner[27] = {0, 0, 0, 1, 1, 2, 2, 3, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3};
+__constant__ int c_seq_row[27] = {1, 4, 7, 4, 7, 4, 7, 4, 7, 2, 3, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9};
+
 // motor model + overheat (rex_gym/model/motor.py:76-143, rex_gym/model/rex.py:601-623) for one joint
 __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, float kp, float kd, float& tau_obs) {
     const float V = 32.0f, R = 0.186f, Kt = 0.0954f;
@@ -287,48 +295,91 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     SV vs; vs.a = fma3(dt, a0.a, L.w); vs.l = fma3(dt, a0.l + cross(L.w, L.vl), L.vl);
     float qs1 = fmaf(dt, qdd1, L.qd[0]), qs2 = fmaf(dt, qdd2, L.qd[1]), qs3 = fmaf(dt, qdd3, L.qd[2]);
 
-    // ---- toe / ground contact: deepest hull sample point ------------------------------------------------
-    const float* TP = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
+    // ---- contact candidates: ONE contact per group = its deepest sample point (same groups/order as the oracle) ----
+    //   foot group  (own lane): foot box corners, then toe hull support points (1 mm margin)
+    //   upper group (own lane): shoulder box corners, then leg box corners
+    //   base group  (owned by lane 0): base + chassis box corners, searched 6 per lane
     float best = 1e30f; V3 rc = mk(0.f, 0.f, 0.f), nrm = mk(0.f, 0.f, 1.f);
-    const int npts = P.cfg.toe_npts;
-    for (int j = 0; j < npts; j++) {
-        V3 r = p3 + mul(R3, mk(TP[3 * j], TP[3 * j + 1], TP[3 * j + 2]));
-        float d; V3 n;
-        ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
-        d -= P.cfg.toe_margin;
-        if (d < best) { best = d; rc = r; nrm = n; }
+    {
+        const float* BX = sm + REXSIM_MT_BOX + leg * 72 + 48;
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            V3 r = p3 + mul(R3, mk(BX[3 * j], BX[3 * j + 1], BX[3 * j + 2]));
+            float d; V3 n;
+            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            if (d < best) { best = d; rc = r; nrm = n; }
+        }
+        const float* TP = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
+        const int npts = P.cfg.toe_npts;
+        for (int j = 0; j < npts; j++) {
+            V3 r = p3 + mul(R3, mk(TP[3 * j], TP[3 * j + 1], TP[3 * j + 2]));
+            float d; V3 n;
+            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            d -= P.cfg.toe_margin;
+            if (d < best) { best = d; rc = r; nrm = n; }
+        }
+    }
+    float bestU = 1e30f; V3 rcU = mk(0.f, 0.f, 0.f), nrmU = mk(0.f, 0.f, 1.f); int kU = 1;
+    {
+        const float* BX = sm + REXSIM_MT_BOX + leg * 72;
+#pragma unroll 1
+        for (int j = 0; j < 16; j++) {
+            const bool sh = j < 8;
+            V3 c = mk(BX[3 * j], BX[3 * j + 1], BX[3 * j + 2]);
+            V3 r = sh ? p1 + mul(R1, c) : p2 + mul(R2, c);
+            float d; V3 n;
+            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            if (d < bestU) { bestU = d; rcU = r; nrmU = n; kU = sh ? 1 : 2; }
+        }
+    }
+    float bestB = 1e30f; V3 rcB = mk(0.f, 0.f, 0.f), nrmB = mk(0.f, 0.f, 1.f);
+    {
+        const float* BB = sm + REXSIM_MT_BASEBOX;
+        int jb = 0;
+#pragma unroll 1
+        for (int jj = 0; jj < 6; jj++) {
+            const int j = 6 * leg + jj;
+            V3 r = mul(R0, mk(BB[3 * j], BB[3 * j + 1], BB[3 * j + 2]));
+            float d; V3 n;
+            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            if (d < bestB) { bestB = d; rcB = r; nrmB = n; jb = j; }
+        }
+        // argmin over the 4 lanes; ties resolve to the lowest point index like the oracle's sequential scan
+        const unsigned m4 = env_mask();
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            float od = __shfl_xor_sync(m4, bestB, o, 4); int oj = __shfl_xor_sync(m4, jb, o, 4);
+            V3 orc = mk(__shfl_xor_sync(m4, rcB.x, o, 4), __shfl_xor_sync(m4, rcB.y, o, 4), __shfl_xor_sync(m4, rcB.z, o, 4));
+            V3 onr = mk(__shfl_xor_sync(m4, nrmB.x, o, 4), __shfl_xor_sync(m4, nrmB.y, o, 4), __shfl_xor_sync(m4, nrmB.z, o, 4));
+            if (od < bestB || (od == bestB && oj < jb)) { bestB = od; jb = oj; rcB = orc; nrmB = onr; }
+        }
     }
     const bool active = best <= 0.0005f;
-    L.contact = active ? 1 : 0;
-    // ---- conditions this fast path does not model: flag loudly ------------------------------------------
+    const bool activeU = bestU <= 0.0005f;
+    const bool activeB = (leg == 0) && (bestB <= 0.0005f);
+    // joint limits (btMultiBodyJointLimitConstraint: a row only while the limit is violated); one row per leg is modelled
+    int limJ = -1; float limSg = 0.f, limPen = 0.f;
     {
-        int e = 0;
-        if (L.q[0] < LB[7] || L.q[0] > LB[14] || L.q[1] < LB[16 + 7] || L.q[1] > LB[16 + 14] || L.q[2] < LB[32 + 7] || L.q[2] > LB[32 + 14])
-            e |= REXSIM_FLAG_JOINT_LIMIT;
-        const float* BX = sm + REXSIM_MT_BOX + leg * 72;
-        float zmin = 1e30f;
-#pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-            float zc1 = p1.z + R1.c0.z * BX[3 * j] + R1.c1.z * BX[3 * j + 1] + R1.c2.z * BX[3 * j + 2];
-            float zc2 = p2.z + R2.c0.z * BX[24 + 3 * j] + R2.c1.z * BX[24 + 3 * j + 1] + R2.c2.z * BX[24 + 3 * j + 2];
-            float zc3 = p3.z + R3.c0.z * BX[48 + 3 * j] + R3.c1.z * BX[48 + 3 * j + 1] + R3.c2.z * BX[48 + 3 * j + 2];
-            zmin = fminf(zmin, fminf(zc1, fminf(zc2, zc3)));
+        int nviol = 0;
+#pragma unroll
+        for (int j = 2; j >= 0; j--) {
+            const float lo = LB[16 * j + 7], hi = LB[16 * j + 14];
+            if (hi - L.q[j] <= 0.f) { limJ = j; limSg = -1.f; limPen = hi - L.q[j]; nviol++; }
+            if (L.q[j] - lo <= 0.f) { limJ = j; limSg = 1.f; limPen = L.q[j] - lo; nviol++; }
         }
-        const float* BB = sm + REXSIM_MT_BASEBOX + (leg % 3) * 24;   // lanes 0..2 check one base/chassis box each
-#pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-            float zc = R0.c0.z * BB[3 * j] + R0.c1.z * BB[3 * j + 1] + R0.c2.z * BB[3 * j + 2];
-            zmin = fminf(zmin, zc);
-        }
-        if (TERRAIN == REXSIM_TERRAIN_PLANE) { if (zmin + L.pos.z <= 0.0005f) e |= REXSIM_FLAG_BODY_CONTACT; }
-        else { if (zmin + L.pos.z <= 0.0005f + 0.03f) e |= REXSIM_FLAG_BODY_CONTACT; }
-        L.err |= e;
+        if (nviol > 1) L.err |= REXSIM_FLAG_JOINT_LIMIT;      // more than one violated limit in a leg: not modelled
     }
-    // any contact in this env?  (skip the solver in flight)
-    const unsigned act_mask = __ballot_sync(0xffffffffu, active);
-    const unsigned env_bits = (act_mask >> ((threadIdx.x & 31) & ~3)) & 0xFu;
+    L.contact = (active ? 1 : 0) | (activeU ? 2 : 0) | (activeB ? 4 : 0);
+    const unsigned envf = or4((active ? 1u : 0u) | ((activeU || activeB || limJ >= 0) ? 2u : 0u));
     float dq1 = 0.f, dq2 = 0.f, dq3 = 0.f; SV dv0; dv0.a = mk(0, 0, 0); dv0.l = mk(0, 0, 0);
-    if (act_mask != 0u) {
+    const float mu = P.cfg.friction, thr = P.cfg.residual_threshold;
+    const int iters = P.cfg.solver_iterations;
+    if (envf == 1u) {
+        // ================= fast path: toe / foot contacts only =============================================
         // ---- constraint rows of the own contact: n, t1, t2 ----------------------------------------------
         V3 t1, t2;
         if (TERRAIN == REXSIM_TERRAIN_PLANE) { t1 = mk(0.f, -1.f, 0.f); t2 = mk(1.f, 0.f, 0.f); }
@@ -339,17 +390,25 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         F[2].a = cross(rc, t2); F[2].l = t2;
         SV v3s = sfma(qs3, S3v, sfma(qs2, S2, sfma(qs1, S1, vs)));   // foot spatial velocity after the free update
         float relv[3] = {sdot(F[0], v3s), sdot(F[1], v3s), sdot(F[2], v3s)};
-        // unit impulse responses of the own rows: inward along the leg, then the base solve
-        float uD1[3], uD2[3], uD3[3]; SV dvb[3];
+        // unit impulse responses of the own rows: inward along the leg gives the base bias g_d, then the base solve
+        float uD1[3], uD2[3], uD3[3]; SV g[3], dvb[3];
+        float Dd[3][3];                // own-leg response with the base held fixed: Dd[r][d] = F_r . w_d
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             SV pD; pD.a = mk(-F[d].a.x, -F[d].a.y, -F[d].a.z); pD.l = mk(-F[d].l.x, -F[d].l.y, -F[d].l.z);
             uD3[d] = -sdot(S3v, pD); pD = sfma(uD3[d] * k3, U3, pD);
             uD2[d] = -sdot(S2, pD); pD = sfma(uD2[d] * k2, U2, pD);
             uD1[d] = -sdot(S1, pD); pD = sfma(uD1[d] * k1, U1, pD);
+            g[d] = pD;
             dvb[d] = neg_mul(Minv, pD);
+            SV w = (uD1[d] * k1) * S1;
+            float e2 = (uD2[d] - sdot(U2, w)) * k2; w = sfma(e2, S2, w);
+            float e3 = (uD3[d] - sdot(U3, w)) * k3; w = sfma(e3, S3v, w);
+            Dd[0][d] = sdot(F[0], w); Dd[1][d] = sdot(F[1], w); Dd[2][d] = sdot(F[2], w);
         }
-        // Delassus rows A[r][3*s+d] = J_r M^-1 J_(s,d)^T : outward pass of every impulse through the own leg
+        // Delassus rows A[r][3*s+d] = J_r M^-1 J_(s,d)^T.  The response of the own foot to a base velocity change b
+        // is T b with T = prod(I - S_i k_i U_i^T), and T^T F_r = -g_r is already known from the inward pass, so a
+        // foreign column costs one 6-dot; own columns add the fixed-base term Dd.
         float A[3][12];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -357,21 +416,14 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             for (int d = 0; d < 3; d++) {
                 SV b = bcast4(dvb[d], s);
                 const bool own = (s == leg);
-                float e1 = ((own ? uD1[d] : 0.f) - sdot(U1, b)) * k1; b = sfma(e1, S1, b);
-                float e2 = ((own ? uD2[d] : 0.f) - sdot(U2, b)) * k2; b = sfma(e2, S2, b);
-                float e3 = ((own ? uD3[d] : 0.f) - sdot(U3, b)) * k3; b = sfma(e3, S3v, b);
-                A[0][3 * s + d] = sdot(F[0], b); A[1][3 * s + d] = sdot(F[1], b); A[2][3 * s + d] = sdot(F[2], b);
+#pragma unroll
+                for (int r = 0; r < 3; r++) A[r][3 * s + d] = (own ? Dd[r][d] : 0.f) - sdot(g[r], b);
             }
         }
         // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
         float den[3], dinv[3], rhs[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float sel = 0.f;
-#pragma unroll
-            for (int s = 0; s < 4; s++) sel = (s == leg) ? A[d][3 * s + d] : sel;
-            den[d] = sel; dinv[d] = 1.0f / sel;
-        }
+        for (int d = 0; d < 3; d++) { den[d] = Dd[d][d] - sdot(g[d], dvb[d]); dinv[d] = 1.0f / den[d]; }
         {
             const float slop = 1e-5f;
             float pen = best + slop;
@@ -382,59 +434,46 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             rhs[2] = -relv[2] * dinv[2];
         }
         // ---- PGS in impulse space, Bullet row order: normals 0..3, then (t1,t2) of contacts 0..3 -----------
-        float lam[12];
-#pragma unroll
-        for (int j = 0; j < 12; j++) lam[j] = 0.f;
-        const float mu = P.cfg.friction, thr = P.cfg.residual_threshold;
-        const int iters = P.cfg.solver_iterations;
-        bool running = env_bits != 0u;   // env has at least one contact
-        for (int it = 0; it < iters; it++) {
-            if (!__any_sync(0xffffffffu, running)) break;
+        // Each lane keeps only its own three impulses and the running row sums rs[d] = sum_j A[d][j] lambda_j;
+        // the owner of a row broadcasts its impulse CHANGE and every lane folds it into its sums (3 FMA).
+        float lam[3] = {0.f, 0.f, 0.f}, rs[3] = {0.f, 0.f, 0.f};
+        bool running = true;             // env-uniform: the 4 lanes of an env leave the loop together
+        const bool mine = active;
+        for (int it = 0; it < iters && running; it++) {
             float resid = 0.f;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                float dvn = 0.f;
-#pragma unroll
-                for (int j = 0; j < 12; j++) dvn = fmaf(A[0][j], lam[j], dvn);
-                float own = 0.f;
-#pragma unroll
-                for (int s2 = 0; s2 < 4; s2++) own = (s2 == leg) ? lam[3 * s2] : own;
-                float dI = rhs[0] - dvn * dinv[0];
-                float sum = own + dI;
-                if (sum < 0.f) { dI = -own; sum = 0.f; }
-                const bool upd = running && active && (leg == s);
-                float nv = upd ? sum : own;
-                if (upd) { float rs = dI * den[0]; resid = fmaxf(resid, rs * rs); }
-                lam[3 * s] = bcast4(nv, s);
+                float dI = rhs[0] - rs[0] * dinv[0];
+                if (lam[0] + dI < 0.f) dI = -lam[0];
+                const bool upd = mine && running && (leg == s);
+                dI = upd ? dI : 0.f;
+                lam[0] += dI;
+                float rr = dI * den[0]; resid = fmaxf(resid, rr * rr);
+                float dl = bcast4(dI, s);
+                rs[0] = fmaf(A[0][3 * s], dl, rs[0]); rs[1] = fmaf(A[1][3 * s], dl, rs[1]); rs[2] = fmaf(A[2][3 * s], dl, rs[2]);
             }
 #pragma unroll
             for (int s = 0; s < 4; s++) {
 #pragma unroll
                 for (int d = 1; d < 3; d++) {
-                    float dvn = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 12; j++) dvn = fmaf(A[d][j], lam[j], dvn);
-                    float own = 0.f, tot = 0.f;
-#pragma unroll
-                    for (int s2 = 0; s2 < 4; s2++) { own = (s2 == leg) ? lam[3 * s2 + d] : own; tot = (s2 == leg) ? lam[3 * s2] : tot; }
-                    float dI = rhs[d] - dvn * dinv[d];
-                    float sum = own + dI;
-                    float lim = mu * tot;
-                    if (sum < -lim) { dI = -lim - own; sum = -lim; }
-                    else if (sum > lim) { dI = lim - own; sum = lim; }
-                    const bool upd = running && active && (leg == s) && (tot > 0.f);
-                    float nv = upd ? sum : own;
-                    if (upd) { float rs = dI * den[d]; resid = fmaxf(resid, rs * rs); }
-                    lam[3 * s + d] = bcast4(nv, s);
+                    float dI = rhs[d] - rs[d] * dinv[d];
+                    const float lim = mu * lam[0];
+                    float sum = lam[d] + dI;
+                    if (sum < -lim) dI = -lim - lam[d];
+                    else if (sum > lim) dI = lim - lam[d];
+                    const bool upd = mine && running && (leg == s) && (lam[0] > 0.f);
+                    dI = upd ? dI : 0.f;
+                    lam[d] += dI;
+                    float rr = dI * den[d]; resid = fmaxf(resid, rr * rr);
+                    float dl = bcast4(dI, s);
+                    rs[0] = fmaf(A[0][3 * s + d], dl, rs[0]); rs[1] = fmaf(A[1][3 * s + d], dl, rs[1]); rs[2] = fmaf(A[2][3 * s + d], dl, rs[2]);
                 }
             }
             resid = max4(resid);
             if (resid <= thr) running = false;
         }
         // ---- apply the net contact impulse: one more response pass -----------------------------------------
-        float ln = 0.f, l1 = 0.f, l2 = 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < 4; s2++) { ln = (s2 == leg) ? lam[3 * s2] : ln; l1 = (s2 == leg) ? lam[3 * s2 + 1] : l1; l2 = (s2 == leg) ? lam[3 * s2 + 2] : l2; }
+        const float ln = lam[0], l1 = lam[1], l2 = lam[2];
         float e1 = ln * uD1[0] + l1 * uD1[1] + l2 * uD1[2];
         float e2 = ln * uD2[0] + l1 * uD2[1] + l2 * uD2[2];
         float e3 = ln * uD3[0] + l1 * uD3[1] + l2 * uD3[2];
@@ -444,6 +483,108 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         dq1 = (e1 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
         dq2 = (e2 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
         dq3 = (e3 - sdot(U3, b)) * k3;
+    }
+    else if (envf & 2u) {
+        // ================= generic path: body contacts and/or a joint limit ====================================
+        // M^-1 of a star-shaped tree = per-leg block + a rank-6 coupling through the base, so no Delassus matrix is
+        // needed: a row's velocity is  J_r dV = -g_r . beta + Jq_r . eps  with beta = base velocity change (replicated
+        // on the 4 lanes) and eps = own-leg joint-rate change at fixed base.  Rows live in local memory (rare path).
+        // rows: 0 = joint limit | 1..3 base contact (lane 0) | 4..6 upper contact | 7..9 foot contact  (n, t1, t2)
+        constexpr int NR = 10;
+        float g_[NR][6], b_[NR][6], Jq_[NR][3], ee_[NR][3], uu_[NR][3], rhs_[NR], dinv_[NR], den_[NR], lam_[NR];
+#pragma unroll 1
+        for (int r = 0; r < NR; r++) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) { g_[r][c] = 0.f; b_[r][c] = 0.f; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { Jq_[r][c] = 0.f; ee_[r][c] = 0.f; uu_[r][c] = 0.f; }
+            rhs_[r] = 0.f; dinv_[r] = 0.f; den_[r] = 0.f; lam_[r] = 0.f;
+        }
+        unsigned actbits = 0u;
+        auto setup_row = [&](int ri, SV Jb, float j0, float j1, float j2) -> float {
+            float relv = sdot(Jb, vs) + j0 * qs1 + j1 * qs2 + j2 * qs3;
+            float u3 = j2; SV pD = (u3 * k3) * U3;
+            float u2 = j1 - sdot(S2, pD); pD = sfma(u2 * k2, U2, pD);
+            float u1 = j0 - sdot(S1, pD); pD = sfma(u1 * k1, U1, pD);
+            SV gg = pD - Jb; SV bb = neg_mul(Minv, gg);
+            float e1 = u1 * k1; SV w = e1 * S1;
+            float e2 = (u2 - sdot(U2, w)) * k2; w = sfma(e2, S2, w);
+            float e3 = (u3 - sdot(U3, w)) * k3;
+            float dn = -sdot(gg, bb) + j0 * e1 + j1 * e2 + j2 * e3;
+            g_[ri][0] = gg.a.x; g_[ri][1] = gg.a.y; g_[ri][2] = gg.a.z; g_[ri][3] = gg.l.x; g_[ri][4] = gg.l.y; g_[ri][5] = gg.l.z;
+            b_[ri][0] = bb.a.x; b_[ri][1] = bb.a.y; b_[ri][2] = bb.a.z; b_[ri][3] = bb.l.x; b_[ri][4] = bb.l.y; b_[ri][5] = bb.l.z;
+            Jq_[ri][0] = j0; Jq_[ri][1] = j1; Jq_[ri][2] = j2;
+            ee_[ri][0] = e1; ee_[ri][1] = e2; ee_[ri][2] = e3;
+            uu_[ri][0] = u1; uu_[ri][1] = u2; uu_[ri][2] = u3;
+            den_[ri] = dn; dinv_[ri] = 1.0f / dn;
+            actbits |= 1u << ri;
+            return relv;
+        };
+        auto setup_contact = [&](int r0, V3 r, V3 n, int kb, float dist) {
+            V3 t1, t2;
+            if (TERRAIN == REXSIM_TERRAIN_PLANE) { t1 = mk(0.f, -1.f, 0.f); t2 = mk(1.f, 0.f, 0.f); }
+            else plane_space(n, t1, t2);
+#pragma unroll 1
+            for (int d = 0; d < 3; d++) {
+                V3 dir = d == 0 ? n : (d == 1 ? t1 : t2);
+                SV F; F.a = cross(r, dir); F.l = dir;
+                float j0 = kb >= 1 ? sdot(S1, F) : 0.f, j1 = kb >= 2 ? sdot(S2, F) : 0.f, j2 = kb >= 3 ? sdot(S3v, F) : 0.f;
+                float relv = setup_row(r0 + d, F, j0, j1, j2);
+                if (d == 0) {
+                    float pen = dist + 1e-5f;
+                    float poserr = 0.f, velerr = -relv;
+                    if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.cfg.erp_contact / dt;
+                    rhs_[r0] = (pen > -0.04f) ? (poserr + velerr) * dinv_[r0] : velerr * dinv_[r0];
+                } else rhs_[r0 + d] = -relv * dinv_[r0 + d];
+            }
+        };
+        if (limJ >= 0) {
+            SV z; z.a = mk(0, 0, 0); z.l = mk(0, 0, 0);
+            float relv = setup_row(0, z, limJ == 0 ? limSg : 0.f, limJ == 1 ? limSg : 0.f, limJ == 2 ? limSg : 0.f);
+            float erp = (limPen > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
+            rhs_[0] = (-limPen * erp / dt - relv) * dinv_[0];
+        }
+        if (activeB) setup_contact(1, rcB, nrmB, 0, bestB);
+        if (activeU) setup_contact(4, rcU, nrmU, kU, bestU);
+        if (active) setup_contact(7, rc, nrm, 3, best);
+        SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);
+        float eps0 = 0.f, eps1 = 0.f, eps2 = 0.f, us0 = 0.f, us1 = 0.f, us2 = 0.f;
+        bool running = true;
+        for (int it = 0; it < iters && running; it++) {
+            float resid = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < 31; t++) {
+                int o, ri;
+                if (t < 4) { o = (it & 1) ? t : 3 - t; ri = 0; }       // limit rows: direction alternates per iteration
+                else { o = c_seq_owner[t - 4]; ri = c_seq_row[t - 4]; }
+                const int ph = (ri == 0) ? 0 : (ri - 1) % 3;            // 0: unilateral row, 1/2: friction row
+                float rsum = Jq_[ri][0] * eps0 + Jq_[ri][1] * eps1 + Jq_[ri][2] * eps2
+                           - (g_[ri][0] * beta.a.x + g_[ri][1] * beta.a.y + g_[ri][2] * beta.a.z + g_[ri][3] * beta.l.x + g_[ri][4] * beta.l.y + g_[ri][5] * beta.l.z);
+                float dI = rhs_[ri] - rsum * dinv_[ri];
+                const float lr = lam_[ri];
+                bool ok = ((actbits >> ri) & 1u) && (leg == o);
+                if (ph == 0) { if (lr + dI < 0.f) dI = -lr; }
+                else {
+                    const float ln = lam_[ri - ph], lim = mu * ln, sum = lr + dI;
+                    if (sum < -lim) dI = -lim - lr; else if (sum > lim) dI = lim - lr;
+                    ok = ok && (ln > 0.f);
+                }
+                dI = ok ? dI : 0.f;
+                lam_[ri] = lr + dI;
+                float rr = dI * den_[ri]; resid = fmaxf(resid, rr * rr);
+                eps0 = fmaf(dI, ee_[ri][0], eps0); eps1 = fmaf(dI, ee_[ri][1], eps1); eps2 = fmaf(dI, ee_[ri][2], eps2);
+                us0 = fmaf(dI, uu_[ri][0], us0); us1 = fmaf(dI, uu_[ri][1], us1); us2 = fmaf(dI, uu_[ri][2], us2);
+                SV dB; dB.a = mk(dI * b_[ri][0], dI * b_[ri][1], dI * b_[ri][2]); dB.l = mk(dI * b_[ri][3], dI * b_[ri][4], dI * b_[ri][5]);
+                beta = beta + bcast4(dB, o);
+            }
+            resid = max4(resid);
+            if (resid <= thr) running = false;
+        }
+        dv0 = beta;
+        SV b = dv0;
+        dq1 = (us0 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
+        dq2 = (us1 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
+        dq3 = (us2 - sdot(U3, b)) * k3;
     }
     // ---- integrate (btMultiBody::stepPositionsMultiDof) --------------------------------------------------
     L.w = vs.a + dv0.a; L.vl = vs.l + dv0.l;
@@ -740,10 +881,9 @@ __device__ __forceinline__ void load_task(const float* sf, const int32_t* si, in
 }
 __device__ __forceinline__ void store_lane(float* sf, int32_t* si, int N, int env, int leg, const Lane& L, const Task& K, bool valid) {
     // shuffles first (all lanes participate), stores predicated on `valid`
-    uint32_t en = L.enabled << (3 * leg);
-    en |= __shfl_xor_sync(0xffffffffu, en, 1, 4); en |= __shfl_xor_sync(0xffffffffu, en, 2, 4);
-    uint32_t ct = (uint32_t)L.contact << leg;
-    ct |= __shfl_xor_sync(0xffffffffu, ct, 1, 4); ct |= __shfl_xor_sync(0xffffffffu, ct, 2, 4);
+    uint32_t en = or4(L.enabled << (3 * leg));
+    // contact mask in the oracle's group numbering: bit 0 base, bit 1+2l upper group of leg l, bit 2+2l foot group
+    uint32_t ct = or4((((uint32_t)L.contact & 1u) << (2 + 2 * leg)) | ((((uint32_t)L.contact >> 1) & 1u) << (1 + 2 * leg)) | (((uint32_t)L.contact >> 2) & 1u));
     if (!valid) return;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -852,7 +992,7 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
 // the fused step kernel
 // -------------------------------------------------------------------------------------------------
 template <int TASK, int SIGNAL, int TERRAIN>
-__global__ void __launch_bounds__(128) step_kernel(const Params P) {
+__global__ void __launch_bounds__(128, REXSIM_MIN_BLOCKS) step_kernel(const Params P) {
     __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
     tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
@@ -944,8 +1084,7 @@ __global__ void __launch_bounds__(128) step_kernel(const Params P) {
     if (valid) finite = write_obs<TASK>(P, env, leg, L, obs_row) && finite;
     finite = (sum4(finite ? 0.f : 1.f) == 0.f);
     if (!finite) { L.err |= REXSIM_FLAG_NONFINITE; done = true; }
-    int err = L.err;
-    err |= __shfl_xor_sync(0xffffffffu, err, 1, 4); err |= __shfl_xor_sync(0xffffffffu, err, 2, 4);
+    int err = (int)or4((unsigned)L.err);
     if (valid && leg == 0) {
         P.reward[env] = reward;
         P.done[env] = done ? 1 : 0;
@@ -1008,8 +1147,7 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
         float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
         // snapshot rows are [NF] / [NI] with N = 1; the 8 replicas computed the same thing, the first one stores
         store_lane(qf, qi, 1, 0, leg, L, K, threadIdx.x < 4);
-        int err = L.err;
-        err |= __shfl_xor_sync(0xffffffffu, err, 1, 4); err |= __shfl_xor_sync(0xffffffffu, err, 2, 4);
+        int err = (int)or4((unsigned)L.err);
         if (threadIdx.x == 0) {
             qf[F_KP] = P.cfg.motor_kp; qf[F_KD] = P.cfg.motor_kd; qf[F_TORIENT] = 0.f; qf[F_IORIENT] = 0.f;
             qi[I_RESETCNT] = 0; qi[I_FIELD] = field;

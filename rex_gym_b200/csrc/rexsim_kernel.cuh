@@ -131,15 +131,26 @@ __device__ __forceinline__ SV crm(SV v, SV m) { SV r; r.a = cross(v.a, m.a); r.l
 __device__ __forceinline__ SV crf(SV v, SV f) { SV r; r.a = cross(v.a, f.a) + cross(v.l, f.l); r.l = cross(v.a, f.l); return r; }
 
 // ----- width-4 (one env) shuffles -------------------------------------------------------------------
-__device__ __forceinline__ float bcast4(float v, int src) { return __shfl_sync(0xffffffffu, v, src, 4); }
+// The member mask names only the 4 lanes of the env: different envs of a warp may diverge (stay-still
+// early-outs, auto-reset, converged solvers) without deadlocking each other's shuffles.
+__device__ __forceinline__ unsigned env_mask() { return 0xFu << ((threadIdx.x & 31u) & ~3u); }
+__device__ __forceinline__ float bcast4(float v, int src) { return __shfl_sync(env_mask(), v, src, 4); }
 __device__ __forceinline__ float sum4(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2, 4);
+    const unsigned m = env_mask();
+    v += __shfl_xor_sync(m, v, 1, 4);
+    v += __shfl_xor_sync(m, v, 2, 4);
     return v;
 }
 __device__ __forceinline__ float max4(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1, 4));
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2, 4));
+    const unsigned m = env_mask();
+    v = fmaxf(v, __shfl_xor_sync(m, v, 1, 4));
+    v = fmaxf(v, __shfl_xor_sync(m, v, 2, 4));
+    return v;
+}
+__device__ __forceinline__ unsigned or4(unsigned v) {
+    const unsigned m = env_mask();
+    v |= __shfl_xor_sync(m, v, 1, 4);
+    v |= __shfl_xor_sync(m, v, 2, 4);
     return v;
 }
 __device__ __forceinline__ V3 sum4(V3 v) { return mk(sum4(v.x), sum4(v.y), sum4(v.z)); }

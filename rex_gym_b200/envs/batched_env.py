@@ -324,8 +324,18 @@ class RexTurnBatchEnv(BatchedRexEnv):
         super().__init__(task="turn", num_envs=num_envs, **kw)
 
 
+class RexStandupBatchEnv(BatchedRexEnv):
+    """rex_gym/envs/gym/standup_env.py:17 RexStandupEnv, batched (starts from INIT_POSES['rest_position'])."""
+
+    def __init__(self, num_envs=1, **kw):
+        kw.setdefault("control_time_step", 0.005); kw.setdefault("action_repeat", 5)
+        kw.setdefault("signal_type", "ol")
+        super().__init__(task="standup", num_envs=num_envs, **kw)
+
+
 # gym ids of rex_gym/playground/__init__.py:17-57 -> batched classes
-ENV_IDS = {"RexWalk-v0": RexWalkBatchEnv, "RexGalloping-v0": RexGallopBatchEnv, "RexTurn-v0": RexTurnBatchEnv}
+ENV_IDS = {"RexWalk-v0": RexWalkBatchEnv, "RexGalloping-v0": RexGallopBatchEnv, "RexTurn-v0": RexTurnBatchEnv,
+           "RexStandup-v0": RexStandupBatchEnv}
 
 
 def make(env_id, num_envs=1, **kwargs):

@@ -95,8 +95,8 @@ def test_static_stand_settles_on_four_toes():
     st = s.state()
     assert 0.200 < st["pos"][2] < 0.210
     assert np.abs(st["qd"]).max() < 0.1 and np.abs(st["linvel"]).max() < 0.02
-    toes = [6, 10, 14, 18]
-    assert e.contact_mask == sum(1 << t for t in toes)      # only the four toe hulls touch
+    toes = [2, 4, 6, 8]
+    assert e.contact_mask == sum(1 << t for t in toes)      # only the four foot groups (toe hulls) touch
     assert e.limit_rows == 0 and 1 <= e.solver_iters <= 60
     q4 = st["quat"]; assert abs(q4[3]) > 0.9999
 
