@@ -79,6 +79,12 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     s->P.cfg.sim_dt = (float)cfg->sim_dt_d;
     const int N = cfg->num_envs;
     s->P.N = N;
+    {
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        s->P.sm_count = sms;
+    }
     s->nsnap = cfg->terrain == REXSIM_TERRAIN_RANDOM ? cfg->nfields : 1;
     CK(cudaMalloc(&s->d_model, REXSIM_MT_FLOATS * sizeof(float)));
     CK(cudaMemcpy(s->d_model, model_tables, REXSIM_MT_FLOATS * sizeof(float), cudaMemcpyHostToDevice));

@@ -8,6 +8,9 @@ namespace rexsim {
 #ifndef REXSIM_MIN_BLOCKS
 #define REXSIM_MIN_BLOCKS 1
 #endif
+#ifndef REXSIM_BLOCK
+#define REXSIM_BLOCK 128
+#endif
 #define PI_F 3.14159265358979323846f
 #define PI_D 3.14159265358979323846
 
@@ -300,51 +303,95 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     //   upper group (own lane): shoulder box corners, then leg box corners
     //   base group  (owned by lane 0): base + chassis box corners, searched 6 per lane
     float best = 1e30f; V3 rc = mk(0.f, 0.f, 0.f), nrm = mk(0.f, 0.f, 1.f);
-    {
-        const float* BX = sm + REXSIM_MT_BOX + leg * 72 + 48;
+    float bestU = 1e30f; V3 rcU = mk(0.f, 0.f, 0.f), nrmU = mk(0.f, 0.f, 1.f); int kU = 1;
+    float bestB = 1e30f; V3 rcB = mk(0.f, 0.f, 0.f), nrmB = mk(0.f, 0.f, 1.f);
+    const float* BXl = sm + REXSIM_MT_BOX + leg * 72;
+    const float* TPl = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
+    const float* BBl = sm + REXSIM_MT_BASEBOX;
+    const int npts = P.cfg.toe_npts;
+    int jb = 0;
+    if (TERRAIN == REXSIM_TERRAIN_PLANE) {
+        // flat ground: the distance is the world z, so the scan needs one row of the rotation (3 FMA per point);
+        // the winning point is reconstructed once afterwards
+        int jf = 0, ju = 0;
+        const V3 z3 = mk(R3.c0.z, R3.c1.z, R3.c2.z), z2 = mk(R2.c0.z, R2.c1.z, R2.c2.z), z1 = mk(R1.c0.z, R1.c1.z, R1.c2.z), z0 = mk(R0.c0.z, R0.c1.z, R0.c2.z);
+#pragma unroll 4
+        for (int j = 0; j < 8; j++) {
+            float d = dot(z3, mk(BXl[48 + 3 * j], BXl[48 + 3 * j + 1], BXl[48 + 3 * j + 2]));
+            if (d < best) { best = d; jf = j; }
+        }
+#pragma unroll 3
+        for (int j = 0; j < npts; j++) {
+            float d = dot(z3, mk(TPl[3 * j], TPl[3 * j + 1], TPl[3 * j + 2])) - P.cfg.toe_margin;
+            if (d < best) { best = d; jf = 8 + j; }
+        }
+        {
+            const float* q = jf < 8 ? BXl + 48 + 3 * jf : TPl + 3 * (jf - 8);
+            rc = p3 + mul(R3, mk(q[0], q[1], q[2]));
+            best += p3.z + L.pos.z;
+        }
+#pragma unroll 4
+        for (int j = 0; j < 16; j++) {
+            const bool sh = j < 8;
+            float d = dot(sh ? z1 : z2, mk(BXl[3 * j], BXl[3 * j + 1], BXl[3 * j + 2])) + (sh ? p1.z : p2.z);
+            if (d < bestU) { bestU = d; ju = j; }
+        }
+        {
+            kU = ju < 8 ? 1 : 2;
+            V3 c = mk(BXl[3 * ju], BXl[3 * ju + 1], BXl[3 * ju + 2]);
+            rcU = kU == 1 ? p1 + mul(R1, c) : p2 + mul(R2, c);
+            bestU += L.pos.z;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 6; jj++) {
+            const int j = 6 * leg + jj;
+            float d = dot(z0, mk(BBl[3 * j], BBl[3 * j + 1], BBl[3 * j + 2]));
+            if (d < bestB) { bestB = d; jb = j; }
+        }
+        {
+            const unsigned m4 = env_mask();
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                float od = __shfl_xor_sync(m4, bestB, o, 4); int oj = __shfl_xor_sync(m4, jb, o, 4);
+                if (od < bestB || (od == bestB && oj < jb)) { bestB = od; jb = oj; }
+            }
+            rcB = mul(R0, mk(BBl[3 * jb], BBl[3 * jb + 1], BBl[3 * jb + 2]));
+            bestB += L.pos.z;
+        }
+    } else {
 #pragma unroll 1
         for (int j = 0; j < 8; j++) {
-            V3 r = p3 + mul(R3, mk(BX[3 * j], BX[3 * j + 1], BX[3 * j + 2]));
+            V3 r = p3 + mul(R3, mk(BXl[48 + 3 * j], BXl[48 + 3 * j + 1], BXl[48 + 3 * j + 2]));
             float d; V3 n;
-            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            if (r.z + L.pos.z > 0.06f) continue;
             ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < best) { best = d; rc = r; nrm = n; }
         }
-        const float* TP = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
-        const int npts = P.cfg.toe_npts;
+#pragma unroll 1
         for (int j = 0; j < npts; j++) {
-            V3 r = p3 + mul(R3, mk(TP[3 * j], TP[3 * j + 1], TP[3 * j + 2]));
+            V3 r = p3 + mul(R3, mk(TPl[3 * j], TPl[3 * j + 1], TPl[3 * j + 2]));
             float d; V3 n;
-            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            if (r.z + L.pos.z > 0.06f) continue;
             ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             d -= P.cfg.toe_margin;
             if (d < best) { best = d; rc = r; nrm = n; }
         }
-    }
-    float bestU = 1e30f; V3 rcU = mk(0.f, 0.f, 0.f), nrmU = mk(0.f, 0.f, 1.f); int kU = 1;
-    {
-        const float* BX = sm + REXSIM_MT_BOX + leg * 72;
 #pragma unroll 1
         for (int j = 0; j < 16; j++) {
             const bool sh = j < 8;
-            V3 c = mk(BX[3 * j], BX[3 * j + 1], BX[3 * j + 2]);
+            V3 c = mk(BXl[3 * j], BXl[3 * j + 1], BXl[3 * j + 2]);
             V3 r = sh ? p1 + mul(R1, c) : p2 + mul(R2, c);
             float d; V3 n;
-            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            if (r.z + L.pos.z > 0.06f) continue;
             ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < bestU) { bestU = d; rcU = r; nrmU = n; kU = sh ? 1 : 2; }
         }
-    }
-    float bestB = 1e30f; V3 rcB = mk(0.f, 0.f, 0.f), nrmB = mk(0.f, 0.f, 1.f);
-    {
-        const float* BB = sm + REXSIM_MT_BASEBOX;
-        int jb = 0;
 #pragma unroll 1
         for (int jj = 0; jj < 6; jj++) {
             const int j = 6 * leg + jj;
-            V3 r = mul(R0, mk(BB[3 * j], BB[3 * j + 1], BB[3 * j + 2]));
+            V3 r = mul(R0, mk(BBl[3 * j], BBl[3 * j + 1], BBl[3 * j + 2]));
             float d; V3 n;
-            if (TERRAIN != REXSIM_TERRAIN_PLANE && r.z + L.pos.z > 0.06f) continue;
+            if (r.z + L.pos.z > 0.06f) continue;
             ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < bestB) { bestB = d; rcB = r; nrmB = n; jb = j; }
         }
@@ -454,20 +501,27 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             }
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-#pragma unroll
-                for (int d = 1; d < 3; d++) {
-                    float dI = rhs[d] - rs[d] * dinv[d];
-                    const float lim = mu * lam[0];
-                    float sum = lam[d] + dI;
-                    if (sum < -lim) dI = -lim - lam[d];
-                    else if (sum > lim) dI = lim - lam[d];
-                    const bool upd = mine && running && (leg == s) && (lam[0] > 0.f);
-                    dI = upd ? dI : 0.f;
-                    lam[d] += dI;
-                    float rr = dI * den[d]; resid = fmaxf(resid, rr * rr);
-                    float dl = bcast4(dI, s);
-                    rs[0] = fmaf(A[0][3 * s + d], dl, rs[0]); rs[1] = fmaf(A[1][3 * s + d], dl, rs[1]); rs[2] = fmaf(A[2][3 * s + d], dl, rs[2]);
-                }
+                // both friction rows of contact s belong to lane s: update t1, fold its change into the own t2 sum
+                // locally, update t2, then broadcast the two changes together (one communication round per contact)
+                const float lim = mu * lam[0];
+                const bool upd = mine && running && (leg == s) && (lam[0] > 0.f);
+                float dI1 = rhs[1] - rs[1] * dinv[1];
+                float sum1 = lam[1] + dI1;
+                if (sum1 < -lim) dI1 = -lim - lam[1]; else if (sum1 > lim) dI1 = lim - lam[1];
+                dI1 = upd ? dI1 : 0.f;
+                lam[1] += dI1;
+                float rs2 = fmaf(A[2][3 * s + 1], dI1, rs[2]);          // own lane: column 3*leg+1 == 3*s+1 when upd
+                float dI2 = rhs[2] - rs2 * dinv[2];
+                float sum2 = lam[2] + dI2;
+                if (sum2 < -lim) dI2 = -lim - lam[2]; else if (sum2 > lim) dI2 = lim - lam[2];
+                dI2 = upd ? dI2 : 0.f;
+                lam[2] += dI2;
+                float r1 = dI1 * den[1], r2 = dI2 * den[2];
+                resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
+                float dl1 = bcast4(dI1, s), dl2 = bcast4(dI2, s);
+                rs[0] = fmaf(A[0][3 * s + 2], dl2, fmaf(A[0][3 * s + 1], dl1, rs[0]));
+                rs[1] = fmaf(A[1][3 * s + 2], dl2, fmaf(A[1][3 * s + 1], dl1, rs[1]));
+                rs[2] = fmaf(A[2][3 * s + 2], dl2, fmaf(A[2][3 * s + 1], dl1, rs[2]));
             }
             resid = max4(resid);
             if (resid <= thr) running = false;
@@ -991,8 +1045,10 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
 // -------------------------------------------------------------------------------------------------
 // the fused step kernel
 // -------------------------------------------------------------------------------------------------
-template <int TASK, int SIGNAL, int TERRAIN>
-__global__ void __launch_bounds__(128, REXSIM_MIN_BLOCKS) step_kernel(const Params P) {
+// OCC = resident CTAs per SM the variant is compiled for: 1 -> 255 registers (lowest latency, small batches),
+// 4 -> 128 registers (16 warps/SM hide the serial PGS / ABA chains, large batches)
+template <int TASK, int SIGNAL, int TERRAIN, int OCC>
+__global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P) {
     __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
     tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
@@ -1181,10 +1237,17 @@ __global__ void set_state_kernel(const Params P, const float* in_f) {
 // -------------------------------------------------------------------------------------------------
 template <int TASK, int SIGNAL>
 static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
-    int threads = 128;
+    int threads = REXSIM_BLOCK;
     int blocks = (P.N * 4 + threads - 1) / threads;
-    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE><<<blocks, threads, 0, st>>>(P);
-    else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM><<<blocks, threads, 0, st>>>(P);
+    // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover)
+    const bool big = blocks > 4 * P.sm_count;
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 4><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1><<<blocks, threads, 0, st>>>(P);
+    } else {
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 4><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1><<<blocks, threads, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_step(const Params& P, cudaStream_t st) {

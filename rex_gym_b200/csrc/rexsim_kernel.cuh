@@ -55,6 +55,7 @@ struct Params {
     int32_t reset_k;
     int32_t settle_snapshot;           // settle kernel: which snapshot this launch produces
     int32_t N;
+    int32_t sm_count;                  // SMs of the device (kernel variant choice)
 };
 
 // ----- tiny vector algebra ---------------------------------------------------------------------------

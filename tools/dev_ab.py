@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
 import rex_gym_b200 as R
 tag = os.environ.get("REXSIM_LIB", "default").split("/")[-1]
-for task, kw in (("walk", dict(target_position=2.0, backwards=False)), ("gallop", dict(signal_type="ol", target_position=2.0)), ("turn", dict())):
+for task, kw in (("walk", dict(target_position=2.0, backwards=False)), ("gallop", dict(signal_type="ol", target_position=2.0))):
     for n in (4096, 65536):
         env = R.BatchedRexEnv(task=task, num_envs=n, normalize=True, auto_reset=True, max_episode_steps=2000, **kw)
         env.reset()
