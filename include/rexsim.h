@@ -51,6 +51,7 @@ enum {
     REXSIM_FLAG_NONFINITE = 1,        /* non-finite state/obs/reward (ConvertTo32Bit raises, wrappers.py:522,542) */
     REXSIM_FLAG_JOINT_LIMIT = 2,      /* more than one joint limit violated in one leg: only one limit row per leg is modelled */
     REXSIM_FLAG_BODY_CONTACT = 4,     /* reserved (body contacts are solved since the generic row path exists) */
+    REXSIM_FLAG_TILE_MISS = 8,        /* a contact query fell outside the 0.8 m heightfield window staged in shared memory */
 };
 
 #define REXSIM_MAX_TOE_PTS 32

@@ -146,20 +146,49 @@ __device__ __forceinline__ SV neg_mul(const Sym6& M, SV p) {   // -(M p)
 }
 
 // ground query --------------------------------------------------------------------------------------
+// Random terrain (rex_gym/model/terrain.py:32-53): every env stages a 16x16-cell (0.8 m x 0.8 m) window of its
+// heightfield, centred on the base, in shared memory once per control step; all contact queries of the step's
+// sub-steps read that tile (4 heights per query) instead of the 256x256 field in L2.
+#define TILE_CELLS 16
+#define TILE_V (TILE_CELLS + 1)          // vertices per side
+#define TILE_STRIDE (TILE_V + 1)         // padded row
+#define TILE_FLOATS (TILE_V * TILE_STRIDE)
+struct Ground { const float* tile; int ix0, iy0; float zoff; int miss; };
+
 template <int TERRAIN>
-__device__ __forceinline__ void ground_query(const Params& P, int field, float zoff, V3 wp, float& dist, V3& n) {
-    if (TERRAIN == REXSIM_TERRAIN_PLANE) { dist = wp.z; n = mk(0.f, 0.f, 1.f); return; }
+__device__ __forceinline__ void load_tile(const Params& P, int field, V3 pos, float* tile, Ground& G, int leg) {
+    G.tile = tile; G.ix0 = 0; G.iy0 = 0; G.zoff = 0.f; G.miss = 0;
+    if (TERRAIN != REXSIM_TERRAIN_RANDOM) return;
     const float* h = P.cfg.fields + (size_t)field * 65536;
+    int cx = (int)floorf(pos.x * 20.0f + 127.5f), cy = (int)floorf(pos.y * 20.0f + 127.5f);
+    G.ix0 = min(max(cx - TILE_CELLS / 2, 0), 255 - TILE_CELLS);
+    G.iy0 = min(max(cy - TILE_CELLS / 2, 0), 255 - TILE_CELLS);
+    G.zoff = P.field_zoff[field];
+    // the 4 lanes of the env copy rows leg, leg+4, ... (17 consecutive floats per row)
+    for (int r = leg; r < TILE_V; r += 4) {
+        const float* src = h + (G.iy0 + r) * 256 + G.ix0;
+#pragma unroll
+        for (int c = 0; c < TILE_V; c++) tile[r * TILE_STRIDE + c] = __ldg(src + c);
+    }
+    __syncwarp(env_mask());
+}
+template <int TERRAIN>
+__device__ __forceinline__ void ground_query(Ground& G, V3 wp, float& dist, V3& n) {
+    if (TERRAIN == REXSIM_TERRAIN_PLANE) { dist = wp.z; n = mk(0.f, 0.f, 1.f); return; }
     const float inv_cell = 20.0f;   // 1/0.05
     float fx = fminf(fmaxf(wp.x * inv_cell + 127.5f, 0.f), 254.999f);
     float fy = fminf(fmaxf(wp.y * inv_cell + 127.5f, 0.f), 254.999f);
     int ixx = (int)floorf(fx), iyy = (int)floorf(fy);
     float u = fx - ixx, v = fy - iyy;
-    float h00 = __ldg(h + iyy * 256 + ixx), h10 = __ldg(h + iyy * 256 + ixx + 1);
-    float h01 = __ldg(h + (iyy + 1) * 256 + ixx), h11 = __ldg(h + (iyy + 1) * 256 + ixx + 1);
+    int lx = ixx - G.ix0, ly = iyy - G.iy0;
+    if (lx < 0 || lx >= TILE_CELLS || ly < 0 || ly >= TILE_CELLS) {      // outside the staged window: flag, clamp
+        G.miss = 1; lx = min(max(lx, 0), TILE_CELLS - 1); ly = min(max(ly, 0), TILE_CELLS - 1);
+    }
+    const float* t = G.tile + ly * TILE_STRIDE + lx;
+    float h00 = t[0], h10 = t[1], h01 = t[TILE_STRIDE], h11 = t[TILE_STRIDE + 1];
     float hx, hy;
     if (v >= u) { hx = h11 - h01; hy = h01 - h00; } else { hx = h10 - h00; hy = h11 - h10; }
-    float hh = h00 + hx * u + hy * v - zoff;
+    float hh = h00 + hx * u + hy * v - G.zoff;
     float nx = -hx * inv_cell, ny = -hy * inv_cell;
     float inv = rsqrtf(nx * nx + ny * ny + 1.f);
     n = mk(nx * inv, ny * inv, inv);
@@ -206,7 +235,7 @@ __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, floa
 // -------------------------------------------------------------------------------------------------
 template <int TERRAIN>
 __device__ __forceinline__ void physics_substep(const Params& P, const float* __restrict__ sm, Lane& L, int leg,
-                                                const float* tau, int field, float zoff) {
+                                                const float* tau, Ground& G) {
     const float dt = (float)P.cfg.sim_dt_d;
     const float* LB = sm + REXSIM_MT_LEG + leg * 48;
     // ---- forward kinematics, world-aligned frame with origin at the base position -------------------
@@ -364,7 +393,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             V3 r = p3 + mul(R3, mk(BXl[48 + 3 * j], BXl[48 + 3 * j + 1], BXl[48 + 3 * j + 2]));
             float d; V3 n;
             if (r.z + L.pos.z > 0.06f) continue;
-            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < best) { best = d; rc = r; nrm = n; }
         }
 #pragma unroll 1
@@ -372,7 +401,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             V3 r = p3 + mul(R3, mk(TPl[3 * j], TPl[3 * j + 1], TPl[3 * j + 2]));
             float d; V3 n;
             if (r.z + L.pos.z > 0.06f) continue;
-            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             d -= P.cfg.toe_margin;
             if (d < best) { best = d; rc = r; nrm = n; }
         }
@@ -383,7 +412,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             V3 r = sh ? p1 + mul(R1, c) : p2 + mul(R2, c);
             float d; V3 n;
             if (r.z + L.pos.z > 0.06f) continue;
-            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < bestU) { bestU = d; rcU = r; nrmU = n; kU = sh ? 1 : 2; }
         }
 #pragma unroll 1
@@ -392,7 +421,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             V3 r = mul(R0, mk(BBl[3 * j], BBl[3 * j + 1], BBl[3 * j + 2]));
             float d; V3 n;
             if (r.z + L.pos.z > 0.06f) continue;
-            ground_query<TERRAIN>(P, field, zoff, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+            ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < bestB) { bestB = d; rcB = r; nrmB = n; jb = j; }
         }
         // argmin over the 4 lanes; ties resolve to the lowest point index like the oracle's sequential scan
@@ -664,7 +693,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
 // Rex.ApplyAction + stepSimulation (rex_gym/model/rex.py:158-163,568-641) for the own leg's three motors
 template <int TERRAIN>
 __device__ __forceinline__ void apply_action_and_step(const Params& P, const float* sm, Lane& L, int leg,
-                                                      const float* cmd, float kp, float kd, int field, float zoff) {
+                                                      const float* cmd, float kp, float kd, Ground& G) {
     float tau[3];
     const uint32_t limit = (uint32_t)(1.0 / P.cfg.sim_dt_d);   // OVERHEAT_SHUTDOWN_TIME / time_step
 #pragma unroll
@@ -678,7 +707,7 @@ __device__ __forceinline__ void apply_action_and_step(const Params& P, const flo
         L.tau_obs[j] = to;
         tau[j] = ((L.enabled >> j) & 1u) ? ta : 0.f;
     }
-    physics_substep<TERRAIN>(P, sm, L, leg, tau, field, zoff);
+    physics_substep<TERRAIN>(P, sm, L, leg, tau, G);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1051,6 +1080,7 @@ template <int TASK, int SIGNAL, int TERRAIN, int OCC>
 __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P) {
     __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ float tiles[TERRAIN == REXSIM_TERRAIN_RANDOM ? (REXSIM_BLOCK / 4) * TILE_FLOATS : 1];
     tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
 
     const int N = P.N;
@@ -1070,7 +1100,8 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     load_task(P.sf, P.si, N, env, K);
     float kp = P.sf[F_KP * (size_t)N + env], kd = P.sf[F_KD * (size_t)N + env];
     int field = P.si[I_FIELD * (size_t)N + env];
-    float zoff = (TERRAIN == REXSIM_TERRAIN_RANDOM) ? P.field_zoff[field] : 0.f;
+    Ground G;
+    load_tile<TERRAIN>(P, field, L.pos, tiles + (TERRAIN == REXSIM_TERRAIN_RANDOM ? (threadIdx.x >> 2) * TILE_FLOATS : 0), G, leg);
 
     // action: ClipAction + RangeNormalize._denormalize_action (wrappers.py:218-236,262-265)
     float act[A];
@@ -1096,9 +1127,10 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // Rex.Step (rex.py:158-163)
     for (int r = 0; r < c.action_repeat; r++) {
-        apply_action_and_step<TERRAIN>(P, sm, L, leg, cmd, kp, kd, field, zoff);
+        apply_action_and_step<TERRAIN>(P, sm, L, leg, cmd, kp, kd, G);
         K.step_counter += 1;
     }
+    if (G.miss) L.err |= REXSIM_FLAG_TILE_MISS;
     // ---- reward (rex_gym_env.py:501-542; turn_env.py:362-367; standup_env.py:151-167) -----------------------
     float reward;
     M3 R = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
@@ -1181,6 +1213,7 @@ template <int TERRAIN>
 __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_f, int32_t* snap_i, int signal, int task) {
     __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ float tiles[TERRAIN == REXSIM_TERRAIN_RANDOM ? 8 * TILE_FLOATS : 1];
     tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
     const int leg = threadIdx.x & 3;
     const int field = P.settle_snapshot;
@@ -1191,14 +1224,15 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     L.ovh = 0u; L.enabled = 7u; L.contact = 0; L.err = 0;
     K.step_counter = 0; K.env_step = 0; K.flags = 0; K.end_step = 0; K.target = 0; K.torient = 0; K.iorient = 0;
     K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
-    float zoff = (TERRAIN == REXSIM_TERRAIN_RANDOM) ? P.field_zoff[field] : 0.f;
+    Ground G;
+    load_tile<TERRAIN>(P, field, L.pos, tiles + (TERRAIN == REXSIM_TERRAIN_RANDOM ? (threadIdx.x >> 2) * TILE_FLOATS : 0), G, leg);
     float stand[3] = {c_pose_stand[0], c_pose_stand[1], c_pose_stand[2]};
     float ip[3];
     if (task == REXSIM_TASK_STANDUP) { ip[0] = (leg & 1) ? 0.4f : -0.4f; ip[1] = -1.5f; ip[2] = 6.f; }
     else init_pose(signal, leg, ip);
-    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, field, zoff);
+    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G);
     const int n2 = (int)(0.5 / P.cfg.sim_dt_d);
-    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, field, zoff);
+    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G);
     {
         float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
         // snapshot rows are [NF] / [NI] with N = 1; the 8 replicas computed the same thing, the first one stores
