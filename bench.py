@@ -145,7 +145,7 @@ def main():
     n = args.envs_per_gpu
     W = max(args.warmup, 3)
     K = args.steps
-    env = R.BatchedRexEnv(num_envs=n, device=f"cuda:{local}", seed=1234 + rank, **WORKLOAD)
+    env = R.BatchedRexEnv(num_envs=n, device=f"cuda:{local}", seed=1234, env_offset=rank * n, **WORKLOAD)
     env.reset()
     A, O = env.action_dim, env.obs_dim
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
@@ -212,6 +212,29 @@ def main():
         ag_us = a.elapsed_time(b) / 20 * 1e3
 
     err = env.check_errors()
+    env.close()
+    # ---- the north-star headline size (65 536 envs per GPU), same workload, device-timed, reported as an extra ----
+    extra = None
+    if n != 65536:
+        nb = 65536
+        envb = R.BatchedRexEnv(num_envs=nb, device=f"cuda:{local}", seed=1234 + rank, env_offset=rank * nb, **WORKLOAD)
+        envb.reset()
+        Kb = min(K, 100)
+        actsb = torch.rand((16, nb, A), device=dev, generator=gen) * 2 - 1
+        for k in range(W):
+            envb.step(actsb[k % 16])
+        barrier()
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kb)]
+        for k in range(Kb):
+            flush.zero_()
+            evb[k][0].record(); envb.step(actsb[k % 16]); evb[k][1].record()
+        barrier()
+        tb = torch.tensor([sum(a.elapsed_time(b) for a, b in evb)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        extra = {"envs_per_gpu": nb, "steps": Kb, "ms_per_step": float(tb.item()) / Kb,
+                 "value": world * nb * Kb / (float(tb.item()) * 1e-3), "unit": "env-steps/s", "error_flags_or": envb.check_errors()}
+        envb.close()
     if rank == 0:
         peaks = {}
         try:
@@ -228,7 +251,7 @@ def main():
             "config": {"workload": f"{n} envs/GPU walk-ik flat terrain, fused ABA+IK+motor kernel (BASELINE configs[1])",
                        "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "wrappers": "ClipAction+RangeNormalize+LimitDuration(2000)+auto-reset fused", "l2": "flushed between timed steps (256 MiB memset)",
-                       "obs_allgather_us": ag_us, "error_flags_or": err},
+                       "obs_allgather_us": ag_us, "error_flags_or": err, "north_star_size": extra},
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * A * 4,
                     "d2h_bytes_per_step": n * (O * 4 + 4 + 1) + 4},
@@ -242,7 +265,6 @@ def main():
         except Exception as e:  # the checker library is test infrastructure; report rather than die
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
