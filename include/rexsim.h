@@ -62,11 +62,14 @@ enum {
 #define REXSIM_MT_BOX (16 + 192 + 384)         /* [4 legs][3 bodies][8 corners][3] collision box corners, body frame */
 #define REXSIM_MT_BASEBOX (16 + 192 + 384 + 288) /* [3 boxes][8][3] base + chassis boxes */
 #define REXSIM_MT_FLOATS (16 + 192 + 384 + 288 + 72)
+#define REXSIM_MT_ARM REXSIM_MT_FLOATS  /* mark 'arm' only: [6 bodies][32]: jpos[3], jrot[9] (child->parent, row-major), axis[3],
+                                         * mass, com[3], inertia[6], lower, upper, pad[5] */
+#define REXSIM_MT_FLOATS_ARM (REXSIM_MT_FLOATS + 192)
 
 typedef struct {
     int32_t num_envs;
     int32_t task, signal, terrain;
-    int32_t num_motors;               /* 12 (mark 'base'); 18 ('arm') not built yet */
+    int32_t num_motors;               /* 12 (mark 'base') or 18 (mark 'arm': model table has REXSIM_MT_FLOATS_ARM floats) */
     int32_t action_repeat;
     int32_t solver_iterations;        /* int(300 / action_repeat) (rex_gym_env.py:25,184) */
     float sim_dt;                     /* control_time_step / action_repeat (unused: sim_dt_d is authoritative) */
@@ -99,7 +102,7 @@ int rexsim_action_dim(int32_t task, int32_t signal);
 /* words per env of the SoA state: float words, int words */
 int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int);
 
-/* model_tables: HOST pointer to REXSIM_MT_FLOATS floats.  Allocates device state, computes the settled
+/* model_tables: HOST pointer to REXSIM_MT_FLOATS (12 motors) or REXSIM_MT_FLOATS_ARM (18 motors) floats.  Allocates device state, computes the settled
  * reset snapshot(s) (600 physics sub-steps, rex.py:314-323) and synchronises. */
 int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_model_floats, RexSim** out);
 void rexsim_destroy(RexSim* sim);

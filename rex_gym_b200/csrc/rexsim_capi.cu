@@ -60,7 +60,9 @@ int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int
 static int validate(const RexSimConfig* c) {
     if (c->num_envs <= 0) return fail(REXSIM_ERR_INVALID, "num_envs must be positive");
     if (c->task < 0 || c->task > 3 || c->signal < 0 || c->signal > 1) return fail(REXSIM_ERR_INVALID, "bad task/signal");
-    if (c->num_motors != 12) return fail(REXSIM_ERR_UNSUPPORTED, "mark='arm' (18 motors) is not built yet");
+    if (c->num_motors != 12 && c->num_motors != 18) return fail(REXSIM_ERR_INVALID, "num_motors must be 12 (base) or 18 (arm)");
+    if (c->num_motors == 18 && !(c->task == REXSIM_TASK_STANDUP || (c->task == REXSIM_TASK_WALK && c->signal == REXSIM_SIGNAL_IK)))
+        return fail(REXSIM_ERR_UNSUPPORTED, "mark='arm' is built for the standup and walk-ik tasks");
     if (c->action_repeat <= 0 || c->solver_iterations <= 0 || !(c->sim_dt_d > 0)) return fail(REXSIM_ERR_INVALID, "bad time stepping");
     if (c->terrain == REXSIM_TERRAIN_RANDOM && (c->nfields <= 0 || !c->fields)) return fail(REXSIM_ERR_INVALID, "random terrain needs a heightfield bank");
     if (c->terrain != REXSIM_TERRAIN_PLANE && c->terrain != REXSIM_TERRAIN_RANDOM) return fail(REXSIM_ERR_UNSUPPORTED, "terrain type");
@@ -70,9 +72,10 @@ static int validate(const RexSimConfig* c) {
 
 int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_model_floats, RexSim** out) {
     if (!cfg || !model_tables || !out) return fail(REXSIM_ERR_INVALID, "null argument");
-    if (n_model_floats != REXSIM_MT_FLOATS) return fail(REXSIM_ERR_MODEL, "model table size mismatch");
     int rc = validate(cfg);
     if (rc) return rc;
+    const int mt_floats = cfg->num_motors == 18 ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS;
+    if (n_model_floats != mt_floats) return fail(REXSIM_ERR_MODEL, "model table size mismatch");
     RexSim* s = new RexSim();
     memset(&s->P, 0, sizeof(Params));
     s->P.cfg = *cfg;
@@ -86,8 +89,8 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
         s->P.sm_count = sms;
     }
     s->nsnap = cfg->terrain == REXSIM_TERRAIN_RANDOM ? cfg->nfields : 1;
-    CK(cudaMalloc(&s->d_model, REXSIM_MT_FLOATS * sizeof(float)));
-    CK(cudaMemcpy(s->d_model, model_tables, REXSIM_MT_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&s->d_model, mt_floats * sizeof(float)));
+    CK(cudaMemcpy(s->d_model, model_tables, mt_floats * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&s->d_sf, (size_t)NF * N * sizeof(float)));
     CK(cudaMalloc(&s->d_si, (size_t)NI * N * sizeof(int32_t)));
     CK(cudaMemset(s->d_sf, 0, (size_t)NF * N * sizeof(float)));

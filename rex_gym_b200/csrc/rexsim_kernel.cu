@@ -1,5 +1,6 @@
 // rexsim_kernel.cu -- sm_100a kernels: fused env step, reset, settle.  See rexsim_kernel.cuh for the design.
 #include "rexsim_kernel.cuh"
+#include "rexsim_arm.cuh"
 #include <math.h>
 
 namespace rexsim {
@@ -233,9 +234,9 @@ __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, floa
 // -------------------------------------------------------------------------------------------------
 // one pybullet.stepSimulation for the 4 lanes of an env (call site rex_gym/model/rex.py:161)
 // -------------------------------------------------------------------------------------------------
-template <int TERRAIN>
+template <int TERRAIN, bool ARM>
 __device__ __forceinline__ void physics_substep(const Params& P, const float* __restrict__ sm, Lane& L, int leg,
-                                                const float* tau, Ground& G) {
+                                                const float* tau, Ground& G, Arm& AR, const float* tauA) {
     const float dt = (float)P.cfg.sim_dt_d;
     const float* LB = sm + REXSIM_MT_LEG + leg * 48;
     // ---- forward kinematics, world-aligned frame with origin at the base position -------------------
@@ -292,6 +293,11 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     SV U1 = mul(IA1, S1); float k1 = 1.0f / sdot(S1, U1); float u1 = tau[0] - sdot(S1, pA1);
     rank1_sub(IA1, U1, k1);
     pA1 = sfma(u1 * k1, U1, pA1 + mul(IA1, cJ1));
+    if (ARM && leg == 0) {   // the arm is a fifth limb of lane 0: fold its articulated inertia into this lane's sum
+        AI Ia; SV pa; SV vb; vb.a = L.w; vb.l = L.vl;
+        arm_inward(sm + REXSIM_MT_ARM, R0, vb, AR, tauA, Ia, pa);
+        add(IA1, Ia); pA1 = pA1 + pa;
+    }
     // ---- base: reduce the 4 legs, add the base body, invert ------------------------------------------
     AI IA0; SV pA0;
     {
@@ -326,6 +332,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     // unconstrained velocities (btMultiBodyDynamicsWorld::solveConstraints: v += a*dt)
     SV vs; vs.a = fma3(dt, a0.a, L.w); vs.l = fma3(dt, a0.l + cross(L.w, L.vl), L.vl);
     float qs1 = fmaf(dt, qdd1, L.qd[0]), qs2 = fmaf(dt, qdd2, L.qd[1]), qs3 = fmaf(dt, qdd3, L.qd[2]);
+    if (ARM && leg == 0) arm_outward(AR, a0, dt);
 
     // ---- contact candidates: ONE contact per group = its deepest sample point (same groups/order as the oracle) ----
     //   foot group  (own lane): foot box corners, then toe hull support points (1 mm margin)
@@ -450,7 +457,26 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         if (nviol > 1) L.err |= REXSIM_FLAG_JOINT_LIMIT;      // more than one violated limit in a leg: not modelled
     }
     L.contact = (active ? 1 : 0) | (activeU ? 2 : 0) | (activeB ? 4 : 0);
-    const unsigned envf = or4((active ? 1u : 0u) | ((activeU || activeB || limJ >= 0) ? 2u : 0u));
+    // arm joint limits (lane 0): bit j set when joint j is outside [lower, upper]; sign +1 lower / -1 upper
+    unsigned armLim = 0u; float armSg[ARM_NJ], armPen[ARM_NJ];
+    if (ARM) {
+#pragma unroll
+        for (int j = 0; j < ARM_NJ; j++) { armSg[j] = 0.f; armPen[j] = 0.f; }
+        if (leg == 0) {
+#pragma unroll
+            for (int j = 0; j < ARM_NJ; j++) {
+                const float lo = sm[REXSIM_MT_ARM + ARM_STRIDE * j + 25], hi = sm[REXSIM_MT_ARM + ARM_STRIDE * j + 26];
+                if (AR.q[j] - lo <= 0.f) { armLim |= 1u << j; armSg[j] = 1.f; armPen[j] = AR.q[j] - lo; }
+                else if (hi - AR.q[j] <= 0.f) { armLim |= 1u << j; armSg[j] = -1.f; armPen[j] = hi - AR.q[j]; }
+            }
+        }
+    }
+    const unsigned envf = or4((active ? 1u : 0u) | ((activeU || activeB || limJ >= 0 || armLim) ? 2u : 0u));
+    float dqA[ARM_NJ];
+    if (ARM) {
+#pragma unroll
+        for (int j = 0; j < ARM_NJ; j++) dqA[j] = 0.f;
+    }
     float dq1 = 0.f, dq2 = 0.f, dq3 = 0.f; SV dv0; dv0.a = mk(0, 0, 0); dv0.l = mk(0, 0, 0);
     const float mu = P.cfg.friction, thr = P.cfg.residual_threshold;
     const int iters = P.cfg.solver_iterations;
@@ -566,6 +592,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         dq1 = (e1 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
         dq2 = (e2 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
         dq3 = (e3 - sdot(U3, b)) * k3;
+        if (ARM && leg == 0) { float z6[ARM_NJ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; arm_apply(AR, dv0, z6, dqA); }
     }
     else if (envf & 2u) {
         // ================= generic path: body contacts and/or a joint limit ====================================
@@ -630,16 +657,54 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         if (activeB) setup_contact(1, rcB, nrmB, 0, bestB);
         if (activeU) setup_contact(4, rcU, nrmU, kU, bestU);
         if (active) setup_contact(7, rc, nrm, 3, best);
+        // arm joint-limit rows (lane 0)
+        float gA_[ARM ? ARM_NJ : 1][6], bA_[ARM ? ARM_NJ : 1][6], eeA_[ARM ? ARM_NJ : 1][ARM_NJ], uuA_[ARM ? ARM_NJ : 1][ARM_NJ];
+        float rhsA_[ARM_NJ], dinvA_[ARM_NJ], denA_[ARM_NJ], lamA_[ARM_NJ], epsA[ARM_NJ], usA[ARM_NJ];
+        if (ARM) {
+#pragma unroll 1
+            for (int j = 0; j < ARM_NJ; j++) {
+                rhsA_[j] = 0.f; dinvA_[j] = 0.f; denA_[j] = 0.f; lamA_[j] = 0.f; epsA[j] = 0.f; usA[j] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 6; c++) { gA_[j][c] = 0.f; bA_[j][c] = 0.f; eeA_[j][c] = 0.f; uuA_[j][c] = 0.f; }
+                if (!((armLim >> j) & 1u)) continue;
+                SV gg; arm_row(AR, j, armSg[j], gg, eeA_[j], uuA_[j]);
+                SV bb = neg_mul(Minv, gg);
+                st6(gA_[j], gg); st6(bA_[j], bb);
+                float dn = -sdot(gg, bb) + armSg[j] * eeA_[j][j];
+                denA_[j] = dn; dinvA_[j] = 1.0f / dn;
+                float relv = armSg[j] * AR.qs[j];
+                float erp = (armPen[j] > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
+                rhsA_[j] = (-armPen[j] * erp / dt - relv) * dinvA_[j];
+            }
+        }
         SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);
         float eps0 = 0.f, eps1 = 0.f, eps2 = 0.f, us0 = 0.f, us1 = 0.f, us2 = 0.f;
         bool running = true;
         for (int it = 0; it < iters && running; it++) {
             float resid = 0.f;
+            constexpr int NLIM = ARM ? 4 + ARM_NJ : 4;       // limit rows in joint order: 4 leg rows (one per lane), then the arm
 #pragma unroll 1
-            for (int t = 0; t < 31; t++) {
+            for (int t = 0; t < NLIM + 27; t++) {
                 int o, ri;
-                if (t < 4) { o = (it & 1) ? t : 3 - t; ri = 0; }       // limit rows: direction alternates per iteration
-                else { o = c_seq_owner[t - 4]; ri = c_seq_row[t - 4]; }
+                if (t < NLIM) {                                     // limit rows: direction alternates per iteration
+                    const int idx = (it & 1) ? t : NLIM - 1 - t;
+                    if (ARM && idx >= 4) {                          // an arm joint-limit row, owned by lane 0
+                        const int j = idx - 4;
+                        float rsumA = armSg[j] * epsA[j] - (gA_[j][0] * beta.a.x + gA_[j][1] * beta.a.y + gA_[j][2] * beta.a.z + gA_[j][3] * beta.l.x + gA_[j][4] * beta.l.y + gA_[j][5] * beta.l.z);
+                        float dIA = rhsA_[j] - rsumA * dinvA_[j];
+                        if (lamA_[j] + dIA < 0.f) dIA = -lamA_[j];
+                        dIA = (((armLim >> j) & 1u) && leg == 0) ? dIA : 0.f;
+                        lamA_[j] += dIA;
+                        float rrA = dIA * denA_[j]; resid = fmaxf(resid, rrA * rrA);
+#pragma unroll
+                        for (int c = 0; c < ARM_NJ; c++) { epsA[c] = fmaf(dIA, eeA_[j][c], epsA[c]); usA[c] = fmaf(dIA, uuA_[j][c], usA[c]); }
+                        SV dBA; dBA.a = mk(dIA * bA_[j][0], dIA * bA_[j][1], dIA * bA_[j][2]); dBA.l = mk(dIA * bA_[j][3], dIA * bA_[j][4], dIA * bA_[j][5]);
+                        beta = beta + bcast4(dBA, 0);
+                        continue;
+                    }
+                    o = idx; ri = 0;
+                }
+                else { o = c_seq_owner[t - NLIM]; ri = c_seq_row[t - NLIM]; }
                 const int ph = (ri == 0) ? 0 : (ri - 1) % 3;            // 0: unilateral row, 1/2: friction row
                 float rsum = Jq_[ri][0] * eps0 + Jq_[ri][1] * eps1 + Jq_[ri][2] * eps2
                            - (g_[ri][0] * beta.a.x + g_[ri][1] * beta.a.y + g_[ri][2] * beta.a.z + g_[ri][3] * beta.l.x + g_[ri][4] * beta.l.y + g_[ri][5] * beta.l.z);
@@ -668,12 +733,17 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         dq1 = (us0 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
         dq2 = (us1 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
         dq3 = (us2 - sdot(U3, b)) * k3;
+        if (ARM && leg == 0) arm_apply(AR, dv0, usA, dqA);
     }
     // ---- integrate (btMultiBody::stepPositionsMultiDof) --------------------------------------------------
     L.w = vs.a + dv0.a; L.vl = vs.l + dv0.l;
     L.qd[0] = qs1 + dq1; L.qd[1] = qs2 + dq2; L.qd[2] = qs3 + dq3;
     L.pos = fma3(dt, L.vl, L.pos);
     L.q[0] = fmaf(dt, L.qd[0], L.q[0]); L.q[1] = fmaf(dt, L.qd[1], L.q[1]); L.q[2] = fmaf(dt, L.qd[2], L.q[2]);
+    if (ARM && leg == 0) {
+#pragma unroll
+        for (int j = 0; j < ARM_NJ; j++) { AR.qd[j] = AR.qs[j] + dqA[j]; AR.q[j] = fmaf(dt, AR.qd[j], AR.q[j]); }
+    }
     {
         float fa = sqrtf(dot(L.w, L.w));
         if (fa * dt > 0.7853981633974483f) fa = 0.5f * 1.5707963267948966f / dt;
@@ -691,10 +761,31 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
 }
 
 // Rex.ApplyAction + stepSimulation (rex_gym/model/rex.py:158-163,568-641) for the own leg's three motors
-template <int TERRAIN>
+__constant__ float c_arm_rest[6] = {-1.6f, -1.6f, 0.f, 0.f, 1.6f, 0.f};   // ARM_POSES['rest'] rex_constants.py:3-8
+
+template <int TERRAIN, bool ARM>
 __device__ __forceinline__ void apply_action_and_step(const Params& P, const float* sm, Lane& L, int leg,
-                                                      const float* cmd, float kp, float kd, Ground& G) {
+                                                      const float* cmd, float kp, float kd, Ground& G, Arm& AR) {
     float tau[3];
+    float tauA[ARM_NJ];
+    if (ARM) {
+#pragma unroll
+        for (int j = 0; j < ARM_NJ; j++) tauA[j] = 0.f;
+        if (leg == 0) {
+            const uint32_t limitA = (uint32_t)(1.0 / P.cfg.sim_dt_d);
+#pragma unroll
+            for (int j = 0; j < ARM_NJ; j++) {
+                float to;
+                float ta = motor_torque(c_arm_rest[j], AR.q[j], AR.qd[j], kp, kd, to);
+                uint32_t w = AR.ovh[j / 3], c = (w >> (10 * (j % 3))) & 1023u;
+                c = (fabsf(ta) > 2.45f) ? min(c + 1u, 1023u) : 0u;
+                if (c > limitA) AR.enabled &= ~(1u << j);
+                AR.ovh[j / 3] = (w & ~(1023u << (10 * (j % 3)))) | (c << (10 * (j % 3)));
+                AR.tau_obs[j] = to;
+                tauA[j] = ((AR.enabled >> j) & 1u) ? ta : 0.f;
+            }
+        }
+    }
     const uint32_t limit = (uint32_t)(1.0 / P.cfg.sim_dt_d);   // OVERHEAT_SHUTDOWN_TIME / time_step
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -707,7 +798,7 @@ __device__ __forceinline__ void apply_action_and_step(const Params& P, const flo
         L.tau_obs[j] = to;
         tau[j] = ((L.enabled >> j) & 1u) ? ta : 0.f;
     }
-    physics_substep<TERRAIN>(P, sm, L, leg, tau, G);
+    physics_substep<TERRAIN, ARM>(P, sm, L, leg, tau, G, AR, tauA);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -993,8 +1084,26 @@ __device__ __forceinline__ void store_lane(float* sf, int32_t* si, int N, int en
     }
 }
 
+// arm state (lane 0 of the env): 6 joint angles / rates, overheat counters, enabled bits
+__device__ __forceinline__ void load_arm(const float* sf, const int32_t* si, int N, int env, Arm& A) {
+#pragma unroll
+    for (int j = 0; j < ARM_NJ; j++) {
+        A.q[j] = sf[(F_AQ + j) * (size_t)N + env]; A.qd[j] = sf[(F_AQD + j) * (size_t)N + env]; A.tau_obs[j] = 0.f;
+    }
+    A.ovh[0] = (uint32_t)si[(I_OVHA + 0) * (size_t)N + env]; A.ovh[1] = (uint32_t)si[(I_OVHA + 1) * (size_t)N + env];
+    A.enabled = ((uint32_t)si[I_FLAGS * (size_t)N + env] >> FL_ARM_ENABLED_SHIFT) & 63u;
+}
+__device__ __forceinline__ void store_arm(float* sf, int32_t* si, int N, int env, const Arm& A) {
+#pragma unroll
+    for (int j = 0; j < ARM_NJ; j++) { sf[(F_AQ + j) * (size_t)N + env] = A.q[j]; sf[(F_AQD + j) * (size_t)N + env] = A.qd[j]; }
+    si[(I_OVHA + 0) * (size_t)N + env] = (int32_t)A.ovh[0]; si[(I_OVHA + 1) * (size_t)N + env] = (int32_t)A.ovh[1];
+    // store_lane (which runs first) wrote the flags word without the arm bits
+    si[I_FLAGS * (size_t)N + env] = (si[I_FLAGS * (size_t)N + env] & ~(63 << FL_ARM_ENABLED_SHIFT)) | (int32_t)(A.enabled << FL_ARM_ENABLED_SHIFT);
+}
+
 // reset one env from the settled snapshot + task draws (BatchEnv.reset -> <task>.reset; rex.py:255-324)
-__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field) {
+template <bool ARM>
+__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field, Arm& AR) {
     const RexSimConfig& c = P.cfg;
     const int N = P.N;
     uint32_t rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env] + 1u;
@@ -1004,6 +1113,7 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
     const int32_t* si = P.snap_i + (size_t)field * NI;
     load_lane(sf, si, 1, 0, leg, L);
     load_task(sf, si, 1, 0, K);
+    if (ARM && leg == 0) load_arm(sf, si, 1, 0, AR);
     K.step_counter = 0; K.env_step = 0; K.end_step = 0;
     K.flags = K.flags & ~((1 << FL_ENABLED_SHIFT) - 1);
     K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
@@ -1076,12 +1186,12 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
 // -------------------------------------------------------------------------------------------------
 // OCC = resident CTAs per SM the variant is compiled for: 1 -> 255 registers (lowest latency, small batches),
 // 4 -> 128 registers (16 warps/SM hide the serial PGS / ABA chains, large batches)
-template <int TASK, int SIGNAL, int TERRAIN, int OCC>
+template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM>
 __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P) {
-    __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
+    __shared__ __align__(16) float sm[ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float tiles[TERRAIN == REXSIM_TERRAIN_RANDOM ? (REXSIM_BLOCK / 4) * TILE_FLOATS : 1];
-    tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
+    tma_load_tables(sm, P.model, (ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS) * 4, &bar);
 
     const int N = P.N;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1095,9 +1205,10 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
                     : (TASK == REXSIM_TASK_TURN) ? 2 : 1;
     const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
 
-    Lane L; Task K;
+    Lane L; Task K; Arm AR;
     load_lane(P.sf, P.si, N, env, leg, L);
     load_task(P.sf, P.si, N, env, K);
+    if (ARM && leg == 0) load_arm(P.sf, P.si, N, env, AR);
     float kp = P.sf[F_KP * (size_t)N + env], kd = P.sf[F_KD * (size_t)N + env];
     int field = P.si[I_FIELD * (size_t)N + env];
     Ground G;
@@ -1127,7 +1238,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // Rex.Step (rex.py:158-163)
     for (int r = 0; r < c.action_repeat; r++) {
-        apply_action_and_step<TERRAIN>(P, sm, L, leg, cmd, kp, kd, G);
+        apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, cmd, kp, kd, G, AR);
         K.step_counter += 1;
     }
     if (G.miss) L.err |= REXSIM_FLAG_TILE_MISS;
@@ -1152,6 +1263,10 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
         float drift = -fabsf(L.pos.y);
         float shake = -fabsf(R.c0.z + R.c1.z);          // rot_matrix[6] + rot_matrix[7]
         float e = L.tau_obs[0] * L.qd[0] + L.tau_obs[1] * L.qd[1] + L.tau_obs[2] * L.qd[2];
+        if (ARM && leg == 0) {
+#pragma unroll
+            for (int j = 0; j < ARM_NJ; j++) e = fmaf(AR.tau_obs[j], AR.qd[j], e);
+        }
         float energy = -fabsf(sum4(e)) * (float)c.sim_dt_d;
         reward = fwd * c.w_distance + energy * c.w_energy + drift * c.w_drift + shake * c.w_shake;
     }
@@ -1180,16 +1295,17 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // ---- auto reset: done envs restart from the settled snapshot; obs = first observation of the new episode --
     if (c.auto_reset && done) {
-        reset_from_snapshot(P, env, leg, L, K, kp, kd, field);
+        reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR);
         if (valid) write_obs<TASK>(P, env, leg, L, obs_row);
     }
     store_lane(P.sf, P.si, N, env, leg, L, K, valid);
+    if (ARM && valid && leg == 0) store_arm(P.sf, P.si, N, env, AR);
 }
 
 // -------------------------------------------------------------------------------------------------
 // reset kernel: BatchEnv.reset(indices)
 // -------------------------------------------------------------------------------------------------
-template <int TASK>
+template <int TASK, bool ARM>
 __global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int j = gid >> 2;
@@ -1199,22 +1315,23 @@ __global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_o
     if (!valid) j = k - 1;
     int env = P.reset_idx ? P.reset_idx[j] : j;
     const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
-    Lane L; Task K; float kp, kd; int field;
-    reset_from_snapshot(P, env, leg, L, K, kp, kd, field);
+    Lane L; Task K; Arm AR; float kp, kd; int field;
+    reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR);
     if (valid && obs_out) write_obs<TASK>(P, env, leg, L, obs_out + (size_t)j * O);
     store_lane(P.sf, P.si, P.N, env, leg, L, K, valid);
+    if (ARM && valid && leg == 0) store_arm(P.sf, P.si, P.N, env, AR);
 }
 
 // -------------------------------------------------------------------------------------------------
 // settle kernel: Rex.Reset (rex.py:296-324) for one snapshot, 4 lanes: 100 sub-steps holding 'stand'
 // then reset_time/dt holding the task's init pose; writes the snapshot row
 // -------------------------------------------------------------------------------------------------
-template <int TERRAIN>
+template <int TERRAIN, bool ARM>
 __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_f, int32_t* snap_i, int signal, int task) {
-    __shared__ __align__(16) float sm[REXSIM_MT_FLOATS];
+    __shared__ __align__(16) float sm[ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float tiles[TERRAIN == REXSIM_TERRAIN_RANDOM ? 8 * TILE_FLOATS : 1];
-    tma_load_tables(sm, P.model, REXSIM_MT_FLOATS * 4, &bar);
+    tma_load_tables(sm, P.model, (ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS) * 4, &bar);
     const int leg = threadIdx.x & 3;
     const int field = P.settle_snapshot;
     Lane L; Task K;
@@ -1222,6 +1339,12 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     L.vl = mk(0, 0, 0); L.w = mk(0, 0, 0);
     for (int j = 0; j < 3; j++) { L.q[j] = c_pose_stand[j]; L.qd[j] = 0.f; L.tau_obs[j] = 0.f; }
     L.ovh = 0u; L.enabled = 7u; L.contact = 0; L.err = 0;
+    Arm AR;
+    if (ARM) {
+#pragma unroll
+        for (int j = 0; j < ARM_NJ; j++) { AR.q[j] = c_arm_rest[j]; AR.qd[j] = 0.f; AR.tau_obs[j] = 0.f; }
+        AR.ovh[0] = 0u; AR.ovh[1] = 0u; AR.enabled = 63u;
+    }
     K.step_counter = 0; K.env_step = 0; K.flags = 0; K.end_step = 0; K.target = 0; K.torient = 0; K.iorient = 0;
     K.G.phi = 0.0; K.G.last_step = 0; K.G.alpha = 0.f;
     Ground G;
@@ -1230,13 +1353,14 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     float ip[3];
     if (task == REXSIM_TASK_STANDUP) { ip[0] = (leg & 1) ? 0.4f : -0.4f; ip[1] = -1.5f; ip[2] = 6.f; }
     else init_pose(signal, leg, ip);
-    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G);
+    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
     const int n2 = (int)(0.5 / P.cfg.sim_dt_d);
-    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G);
+    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
     {
         float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
         // snapshot rows are [NF] / [NI] with N = 1; the 8 replicas computed the same thing, the first one stores
         store_lane(qf, qi, 1, 0, leg, L, K, threadIdx.x < 4);
+        if (ARM && threadIdx.x == 0) store_arm(qf, qi, 1, 0, AR);
         int err = (int)or4((unsigned)L.err);
         if (threadIdx.x == 0) {
             qf[F_KP] = P.cfg.motor_kp; qf[F_KD] = P.cfg.motor_kd; qf[F_TORIENT] = 0.f; qf[F_IORIENT] = 0.f;
@@ -1253,7 +1377,12 @@ __global__ void get_state_kernel(const Params P, float* out_f, int32_t* out_i) {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= P.N) return;
     const size_t N = P.N;
-    for (int w = 0; w < 37; w++) out_f[w * N + env] = P.sf[w * N + env];
+    const int nm = P.cfg.num_motors;
+    for (int w = 0; w < 13; w++) out_f[w * N + env] = P.sf[w * N + env];
+    for (int j = 0; j < nm; j++) {
+        out_f[(13 + j) * N + env] = P.sf[(j < 12 ? F_Q + j : F_AQ + j - 12) * N + env];
+        out_f[(13 + nm + j) * N + env] = P.sf[(j < 12 ? F_QD + j : F_AQD + j - 12) * N + env];
+    }
     out_i[0 * N + env] = P.si[I_STEP * N + env];
     out_i[1 * N + env] = P.si[I_ENVSTEP * N + env];
     out_i[2 * N + env] = P.si[I_FLAGS * N + env];
@@ -1263,26 +1392,40 @@ __global__ void set_state_kernel(const Params P, const float* in_f) {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= P.N) return;
     const size_t N = P.N;
-    for (int w = 0; w < 37; w++) P.sf[w * N + env] = in_f[w * N + env];
+    const int nm = P.cfg.num_motors;
+    for (int w = 0; w < 13; w++) P.sf[w * N + env] = in_f[w * N + env];
+    for (int j = 0; j < nm; j++) {
+        P.sf[(j < 12 ? F_Q + j : F_AQ + j - 12) * N + env] = in_f[(13 + j) * N + env];
+        P.sf[(j < 12 ? F_QD + j : F_AQD + j - 12) * N + env] = in_f[(13 + nm + j) * N + env];
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
 // host-side launchers (called from rexsim_capi.cu)
 // -------------------------------------------------------------------------------------------------
-template <int TASK, int SIGNAL>
-static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
+template <int TASK, int SIGNAL, bool ARM>
+static cudaError_t launch_step_tsa(const Params& P, cudaStream_t st) {
     int threads = REXSIM_BLOCK;
     int blocks = (P.N * 4 + threads - 1) / threads;
     // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover)
-    const bool big = blocks > 4 * P.sm_count;
+    const bool big = !ARM && blocks > 4 * P.sm_count;
     if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 4><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1><<<blocks, threads, 0, st>>>(P);
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM><<<blocks, threads, 0, st>>>(P);
     } else {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 4><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1><<<blocks, threads, 0, st>>>(P);
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM><<<blocks, threads, 0, st>>>(P);
     }
     return cudaGetLastError();
+}
+template <int TASK, int SIGNAL>
+static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
+    // the arm (mark='arm') is built for the standup task (BASELINE config 5) and the walk task
+    if (P.cfg.num_motors == 18) {
+        if (TASK == REXSIM_TASK_STANDUP || (TASK == REXSIM_TASK_WALK && SIGNAL == REXSIM_SIGNAL_IK)) return launch_step_tsa<TASK, SIGNAL, (TASK == REXSIM_TASK_STANDUP || (TASK == REXSIM_TASK_WALK && SIGNAL == REXSIM_SIGNAL_IK))>(P, st);
+        return cudaErrorNotSupported;
+    }
+    return launch_step_tsa<TASK, SIGNAL, false>(P, st);
 }
 cudaError_t launch_step(const Params& P, cudaStream_t st) {
     const int t = P.cfg.task, s = P.cfg.signal;
@@ -1295,13 +1438,21 @@ cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st) {
     int k = P.reset_idx ? P.reset_k : P.N;
     if (k <= 0) return cudaSuccess;
     int threads = 128, blocks = (k * 4 + threads - 1) / threads;
-    if (P.cfg.task == REXSIM_TASK_GALLOP) reset_kernel<REXSIM_TASK_GALLOP><<<blocks, threads, 0, st>>>(P, obs_out);
-    else reset_kernel<REXSIM_TASK_WALK><<<blocks, threads, 0, st>>>(P, obs_out);
+    const bool arm = P.cfg.num_motors == 18;
+    if (P.cfg.task == REXSIM_TASK_GALLOP) reset_kernel<REXSIM_TASK_GALLOP, false><<<blocks, threads, 0, st>>>(P, obs_out);
+    else if (arm) reset_kernel<REXSIM_TASK_WALK, true><<<blocks, threads, 0, st>>>(P, obs_out);
+    else reset_kernel<REXSIM_TASK_WALK, false><<<blocks, threads, 0, st>>>(P, obs_out);
     return cudaGetLastError();
 }
 cudaError_t launch_settle(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st) {
-    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) settle_kernel<REXSIM_TERRAIN_PLANE><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
-    else settle_kernel<REXSIM_TERRAIN_RANDOM><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    const bool arm = P.cfg.num_motors == 18;
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
+        if (arm) settle_kernel<REXSIM_TERRAIN_PLANE, true><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+        else settle_kernel<REXSIM_TERRAIN_PLANE, false><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    } else {
+        if (arm) settle_kernel<REXSIM_TERRAIN_RANDOM, true><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+        else settle_kernel<REXSIM_TERRAIN_RANDOM, false><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_get_state(const Params& P, float* out_f, int32_t* out_i, cudaStream_t st) {

@@ -26,15 +26,18 @@ namespace rexsim {
 // ----- SoA state word indices ---------------------------------------------------------------------
 enum {
     F_POS = 0, F_QUAT = 3, F_LINVEL = 7, F_ANGVEL = 10, F_Q = 13, F_QD = 25,
-    F_ALPHA = 37, F_TARGET = 38, F_TORIENT = 39, F_IORIENT = 40, F_KP = 41, F_KD = 42, NF = 43
+    F_ALPHA = 37, F_TARGET = 38, F_TORIENT = 39, F_IORIENT = 40, F_KP = 41, F_KD = 42,
+    F_AQ = 43, F_AQD = 49, NF = 55      // arm joint angles / rates (mark='arm'; unused words otherwise)
 };
 enum {
     I_STEP = 0, I_ENVSTEP = 1, I_FLAGS = 2, I_RESETCNT = 3, I_FIELD = 4, I_ENDSTEP = 5, I_GPLAST = 6,
-    I_PHI_LO = 7, I_PHI_HI = 8, I_OVH = 9 /*4 words, 3x10-bit counters per leg*/, I_CONTACT = 13, NI = 14
+    I_PHI_LO = 7, I_PHI_HI = 8, I_OVH = 9 /*4 words, 3x10-bit counters per leg*/, I_CONTACT = 13,
+    I_OVHA = 14 /*2 words, 3x10-bit counters of the arm motors*/, NI = 16
 };
 enum {
     FL_GOAL = 1, FL_TERMINATING = 2, FL_STILL = 4, FL_BACKWARDS = 8, FL_CLOCKWISE = 16, FL_ENVGOAL = 32,
-    FL_ENABLED_SHIFT = 8   // 12 motor-enabled bits
+    FL_ENABLED_SHIFT = 8,  // 12 leg motor-enabled bits
+    FL_ARM_ENABLED_SHIFT = 20   // 6 arm motor-enabled bits
 };
 
 struct Params {

@@ -48,7 +48,10 @@ class _Info(object):
 
     def __getitem__(self, i):
         if self._cmd is None:
-            self._cmd = self._env.last_command().t().contiguous().cpu().numpy()
+            c = self._env.last_command().t().contiguous().cpu().numpy()
+            if self._env.num_motors == 18:          # the arm holds ARM_POSES['rest'] (rex_gym_env.py:363-367)
+                c = np.concatenate([c, np.tile(np.array([-1.6, -1.6, 0., 0., 1.6, 0.], np.float32), (c.shape[0], 1))], axis=1)
+            self._cmd = c
         return {"action": self._cmd[i]}
 
 
@@ -98,7 +101,9 @@ class BatchedRexEnv(object):
         cts = control_time_step or (0.006 if task == "gallop" else 0.005)
         self.control_time_step, self._action_repeat = cts, rep
         self._time_step = cts / rep
-        tables, toe_npts = pack_model_tables(mark if mark == "base" else "base")
+        if mark not in ("base", "arm"):
+            raise ValueError("mark must be 'base' or 'arm'")          # mark_constants.py:1
+        tables, toe_npts = pack_model_tables(mark)
         c = _capi.RexSimConfig()
         c.num_envs, c.task, c.signal, c.terrain = self.num_envs, TASKS[task], SIGNALS[signal_type], TERRAINS[terrain_type]
         c.num_motors, c.action_repeat = self.num_motors, rep
@@ -249,7 +254,7 @@ class BatchedRexEnv(object):
     # ---- extras ------------------------------------------------------------------------------------
     def get_state(self):
         """Physical state of every env (pybullet getBasePositionAndOrientation/getBaseVelocity/getJointState)."""
-        N, nm = self.num_envs, 12
+        N, nm = self.num_envs, self.num_motors
         f = torch.zeros((13 + 2 * nm, N), dtype=torch.float32, device=self.device)
         i = torch.zeros((4, N), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
@@ -260,7 +265,7 @@ class BatchedRexEnv(object):
                     step_counter=i[0].copy(), env_step_counter=i[1].copy(), flags=i[2].copy(), contact_mask=i[3].copy())
 
     def set_state(self, pos, quat, linvel, angvel, q, qd):
-        N, nm = self.num_envs, 12
+        N, nm = self.num_envs, self.num_motors
         f = np.concatenate([np.asarray(x, np.float32).reshape(N, -1).T for x in (pos, quat, linvel, angvel, q, qd)], axis=0)
         t = torch.from_numpy(np.ascontiguousarray(f)).to(self.device)
         with torch.cuda.device(self.device):

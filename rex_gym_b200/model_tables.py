@@ -8,8 +8,18 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MT_BASE, MT_LEG, MT_TOE, MT_BOX, MT_BASEBOX, MT_FLOATS = 0, 16, 208, 592, 880, 952
+MT_ARM, ARM_STRIDE, MT_FLOATS_ARM = 952, 32, 952 + 192
 MAX_TOE_PTS = 32
 TOE_MARGIN = 0.001   # Bullet's URDF importer puts a 1 mm collision margin on convex hulls
+
+
+def _rpy_to_mat(rpy):
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return rz @ ry @ rx          # URDF fixed-axis roll, pitch, yaw
 
 
 def _sym6(I):
@@ -29,7 +39,10 @@ def pack_model_tables(mark="base"):
     bodies = j["bodies"]
     if len(bodies) < 13:
         raise ValueError("model must have a base and four 3-joint legs")
-    t = np.zeros(MT_FLOATS, dtype=np.float64)
+    arm = mark == "arm"
+    if arm and len(bodies) != 19:
+        raise ValueError("arm model must have six arm bodies after the legs")
+    t = np.zeros(MT_FLOATS_ARM if arm else MT_FLOATS, dtype=np.float64)
     b0 = bodies[0]
     t[MT_BASE + 0] = b0["mass"]
     t[MT_BASE + 1:MT_BASE + 4] = b0["com"]
@@ -73,4 +86,17 @@ def pack_model_tables(mark="base"):
                     raise ValueError("toe hulls must have the same number (<=32) of sample points")
                 ot = MT_TOE + 3 * MAX_TOE_PTS * leg
                 t[ot:ot + 3 * npts] = pts.reshape(-1)
+    if arm:
+        for k in range(6):
+            b = bodies[13 + k]
+            if b["parent"] != (0 if k == 0 else 12 + k):
+                raise ValueError("the arm must be one serial chain attached to the base")
+            o = MT_ARM + ARM_STRIDE * k
+            t[o:o + 3] = b["joint_xyz"]
+            t[o + 3:o + 12] = _rpy_to_mat(b["joint_rpy"]).reshape(-1)      # child -> parent, row-major
+            t[o + 12:o + 15] = b["axis"]
+            t[o + 15] = b["mass"]
+            t[o + 16:o + 19] = b["com"]
+            t[o + 19:o + 25] = _sym6(b["inertia"])
+            t[o + 25], t[o + 26] = b["lower"], b["upper"]
     return t.astype(np.float32), int(npts)

@@ -35,7 +35,7 @@ def test_host_only_entry_points():
     cfg = _capi.RexSimConfig()
     nf, ni = C.c_int32(), C.c_int32()
     assert L.rexsim_state_words(C.byref(cfg), C.byref(nf), C.byref(ni)) == 0
-    assert nf.value == 43 and ni.value == 14
+    assert nf.value == 55 and ni.value == 16
 
 
 def test_create_rejects_bad_arguments_without_touching_the_gpu():
@@ -44,10 +44,11 @@ def test_create_rejects_bad_arguments_without_touching_the_gpu():
     cfg = _capi.RexSimConfig()
     h = C.c_void_p()
     tb = np.zeros(952, np.float32)
-    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 951, C.byref(h)) == -2          # model size
     assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -1          # num_envs = 0
-    cfg.num_envs, cfg.num_motors, cfg.task = 8, 18, 0
-    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -4          # arm not built
+    cfg.num_envs, cfg.num_motors, cfg.task, cfg.action_repeat, cfg.solver_iterations, cfg.sim_dt_d, cfg.toe_npts = 8, 12, 0, 5, 60, 0.001, 27
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 951, C.byref(h)) == -2          # model table size
+    cfg.num_motors, cfg.task = 18, 1
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952 + 192, C.byref(h)) == -4    # arm + gallop not built
     assert b"arm" in L.rexsim_last_error()
     with pytest.raises(ValueError):
         _capi.check(-4)
