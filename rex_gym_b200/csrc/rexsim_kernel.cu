@@ -351,10 +351,15 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         // the winning point is reconstructed once afterwards
         int jf = 0, ju = 0;
         const V3 z3 = mk(R3.c0.z, R3.c1.z, R3.c2.z), z2 = mk(R2.c0.z, R2.c1.z, R2.c2.z), z1 = mk(R1.c0.z, R1.c1.z, R1.c2.z), z0 = mk(R0.c0.z, R0.c1.z, R0.c2.z);
+        // conservative reach bounds (largest corner distance from the body origin, from the URDF boxes): a group whose
+        // body origin is higher than its reach cannot touch z = 0, so its scan is skipped (standing / walking: all three)
+        const float zf = p3.z + L.pos.z, zs = p1.z + L.pos.z, zl = p2.z + L.pos.z;
+        if (zf < 0.115f) {
 #pragma unroll 4
-        for (int j = 0; j < 8; j++) {
-            float d = dot(z3, mk(BXl[48 + 3 * j], BXl[48 + 3 * j + 1], BXl[48 + 3 * j + 2]));
-            if (d < best) { best = d; jf = j; }
+            for (int j = 0; j < 8; j++) {
+                float d = dot(z3, mk(BXl[48 + 3 * j], BXl[48 + 3 * j + 1], BXl[48 + 3 * j + 2]));
+                if (d < best) { best = d; jf = j; }
+            }
         }
 #pragma unroll 3
         for (int j = 0; j < npts; j++) {
@@ -366,25 +371,25 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             rc = p3 + mul(R3, mk(q[0], q[1], q[2]));
             best += p3.z + L.pos.z;
         }
+        if (zs < 0.05f || zl < 0.12f) {
 #pragma unroll 4
-        for (int j = 0; j < 16; j++) {
-            const bool sh = j < 8;
-            float d = dot(sh ? z1 : z2, mk(BXl[3 * j], BXl[3 * j + 1], BXl[3 * j + 2])) + (sh ? p1.z : p2.z);
-            if (d < bestU) { bestU = d; ju = j; }
-        }
-        {
+            for (int j = 0; j < 16; j++) {
+                const bool sh = j < 8;
+                float d = dot(sh ? z1 : z2, mk(BXl[3 * j], BXl[3 * j + 1], BXl[3 * j + 2])) + (sh ? p1.z : p2.z);
+                if (d < bestU) { bestU = d; ju = j; }
+            }
             kU = ju < 8 ? 1 : 2;
             V3 c = mk(BXl[3 * ju], BXl[3 * ju + 1], BXl[3 * ju + 2]);
             rcU = kU == 1 ? p1 + mul(R1, c) : p2 + mul(R2, c);
             bestU += L.pos.z;
         }
+        if (L.pos.z < 0.19f) {          // env-uniform: the base pose is replicated on the 4 lanes
 #pragma unroll
-        for (int jj = 0; jj < 6; jj++) {
-            const int j = 6 * leg + jj;
-            float d = dot(z0, mk(BBl[3 * j], BBl[3 * j + 1], BBl[3 * j + 2]));
-            if (d < bestB) { bestB = d; jb = j; }
-        }
-        {
+            for (int jj = 0; jj < 6; jj++) {
+                const int j = 6 * leg + jj;
+                float d = dot(z0, mk(BBl[3 * j], BBl[3 * j + 1], BBl[3 * j + 2]));
+                if (d < bestB) { bestB = d; jb = j; }
+            }
             const unsigned m4 = env_mask();
 #pragma unroll
             for (int o = 1; o < 4; o <<= 1) {
@@ -849,13 +854,14 @@ template <bool ROT>
 __device__ __forceinline__ void ik_signal(GaitState& G, bool gallop, int step_counter, double dtd, int leg,
                                           float base_x, float base_z, float v, float w_rot, double T, float direction, float* cmd) {
     const int il = leg ^ 1;
-    double now = step_counter * dtd;
+    // fp64 timing must round exactly like the reference's Python floats: no FMA contraction (a - b*c is NOT fused)
+    double now = __dmul_rn((double)step_counter, dtd);
     if (T <= 0.01) T = 0.01;
     if (G.phi >= 0.99) G.last_step = step_counter;
-    G.phi = (now - G.last_step * dtd) / T;
+    G.phi = __ddiv_rn(__dsub_rn(now, __dmul_rn((double)G.last_step, dtd)), T);
     double off = gallop ? ((il >= 2) ? 0.8 : 0.0) : ((il == 1 || il == 2) ? 0.5 : 0.0);
-    double ph = G.phi + off;
-    if (ph >= 1) ph = ph - 1.;
+    double ph = __dadd_rn(G.phi, off);
+    if (ph >= 1) ph = __dsub_rn(ph, 1.);
     const bool stance = ph <= 0.5;
     float phase = stance ? (float)(ph / 0.5) : (float)((ph - 0.5) / (1 - 0.5));
     float SX = 0.f, SZ = 0.f;
@@ -909,7 +915,7 @@ struct Task {
 template <int TASK, int SIGNAL>
 __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lane& L, int leg, const float* act, float* cmd) {
     const double dtd = P.cfg.sim_dt_d;
-    const double t = K.step_counter * dtd;
+    const double t = __dmul_rn((double)K.step_counter, dtd);     // products via __dmul_rn: never contracted into FMAs
     float ip[3]; init_pose(SIGNAL, leg, ip);
     if (TASK == REXSIM_TASK_WALK) {                                   // envs/gym/walk_env.py:207-324
         if (K.flags & FL_STILL) { cmd[0] = ip[0]; cmd[1] = ip[1]; cmd[2] = ip[2]; return; }
@@ -919,7 +925,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
                 if (!(K.flags & FL_TERMINATING)) { K.end_step = K.step_counter; K.flags |= FL_TERMINATING; }
             }
         }
-        const double end_t = K.end_step * dtd;
+        const double end_t = __dmul_rn((double)K.end_step, dtd);
         if (SIGNAL == REXSIM_SIGNAL_IK) {
             double p = 0.8 + (double)act[0];
             double gait = (0.0 <= t && t <= p) ? t : 1.0;
@@ -958,7 +964,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
                 if (!(K.flags & FL_TERMINATING)) { K.end_step = K.step_counter; K.flags |= FL_TERMINATING; }
             }
         }
-        const double end_t = K.end_step * dtd;
+        const double end_t = __dmul_rn((double)K.end_step, dtd);
         if (SIGNAL == REXSIM_SIGNAL_IK) {
             double p = 1. + (double)act[1];
             double gait = (0.0 <= t && t <= p) ? t : 1.0;
@@ -980,7 +986,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
         }
     } else if (TASK == REXSIM_TASK_TURN) {                            // envs/gym/turn_env.py:230-346
         if (K.flags & FL_STILL) {
-            if (t - K.end_step * dtd >= 1.) K.flags |= FL_ENVGOAL;
+            if (__dsub_rn(t, __dmul_rn((double)K.end_step, dtd)) >= 1.) K.flags |= FL_ENVGOAL;
             cmd[0] = ip[0]; cmd[1] = ip[1]; cmd[2] = ip[2];
             return;
         }
@@ -995,7 +1001,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
         }
         if (SIGNAL == REXSIM_SIGNAL_IK) {
             double gait = (0.0 <= t && t <= .8) ? t : 1.0;
-            double dirv = -0.5 * gait;
+            double dirv = __dmul_rn(-0.5, gait);
             if (K.flags & FL_CLOCKWISE) dirv *= -1;
             float step_rotation = (float)(dirv + (double)act[0]);
             double step_period = 0.75 + (double)act[1];

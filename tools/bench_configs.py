@@ -13,6 +13,7 @@ CONFIGS = [
     ("C4 turn-ik heightfield 16384 (per-GPU share of 65536 on 4)", dict(task="turn", num_envs=16384, signal_type="ik", terrain_type="random", num_fields=64)),
     ("C4' turn-ik heightfield 65536 on one GPU", dict(task="turn", num_envs=65536, signal_type="ik", terrain_type="random", num_fields=64)),
     ("standup (base mark) 16384", dict(task="standup", num_envs=16384, signal_type="ol")),
+    ("C5 standup arm (18-DOF) 16384 (per-GPU share of 131072 on 8)", dict(task="standup", num_envs=16384, signal_type="ol", mark="arm")),
 ]
 
 def main():

@@ -27,10 +27,10 @@ def run(task, signal, n, steps, terrain="plane", **kw):
         sg = env.get_state()
         eq = np.array([np.abs(sg['q'][i] - ora.state(i)['q']).max() for i in range(n)])
         ep = np.array([np.abs(sg['pos'][i] - ora.state(i)['pos']).max() for i in range(n)])
-        cm = np.array([(ora.env(i).contact_mask >> 6 & 1) | ((ora.env(i).contact_mask >> 10 & 1) << 1) | ((ora.env(i).contact_mask >> 14 & 1) << 2) | ((ora.env(i).contact_mask >> 18 & 1) << 3) for i in range(n)])
+        cm = np.array([ora.env(i).contact_mask & 0x1FF for i in range(n)])
         mism = (cm != sg['contact_mask']) & alive
         worst_q = max(worst_q, eq[alive].max() if alive.any() else 0); worst_p = max(worst_p, ep[alive].max() if alive.any() else 0)
-        if k % 50 == 0 or k == steps - 1:
+        if k % 100 == 0 or k == steps - 1:
             print(f"  step {k:4d} alive {alive.sum():3d} max|dq| {eq[alive].max() if alive.any() else 0:.2e} max|dpos| {ep[alive].max() if alive.any() else 0:.2e} "
                   f"|dobs| {np.abs(og-oc)[alive].max() if alive.any() else 0:.2e} |drew| {np.abs(rg-rc)[alive].max() if alive.any() else 0:.2e} contact mismatches {mism.sum()} done g/c {dg.sum()}/{dc.sum()}")
         newly = (dg | dc) & alive
@@ -44,8 +44,8 @@ def run(task, signal, n, steps, terrain="plane", **kw):
 
 if __name__ == "__main__":
     t = time.time()
-    run("walk", "ik", 32, 400, target_position=2.0, backwards=False)
-    run("walk", "ik", 32, 600, target_position=2.0, backwards=True)
-    run("gallop", "ol", 32, 300, target_position=2.0)
-    run("turn", "ik", 32, 300)
+    run("walk", "ik", 32, 1000, target_position=3.0, backwards=True)
+    run("gallop", "ol", 32, 400, target_position=2.0)
+    run("gallop", "ik", 32, 300, target_position=2.0)
+    run("turn", "ik", 32, 400)
     print("elapsed", time.time() - t)
