@@ -684,15 +684,35 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         }
         SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);
         float eps0 = 0.f, eps1 = 0.f, eps2 = 0.f, us0 = 0.f, us1 = 0.f, us2 = 0.f;
+        // compact the Gauss-Seidel sequence to the rows that exist in this env (env-uniform: built from shuffled bits)
+        constexpr int NLIM = ARM ? 4 + ARM_NJ : 4;       // limit rows in joint order: 4 leg rows (one per lane), then the arm
+        unsigned char llist[NLIM], clist[27];
+        int nl = 0, nc = 0;
+        {
+            unsigned actAll[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) actAll[o] = __shfl_sync(env_mask(), actbits, o, 4);
+            const unsigned armAll = ARM ? __shfl_sync(env_mask(), armLim, 0, 4) : 0u;
+#pragma unroll
+            for (int idx = 0; idx < NLIM; idx++) {
+                const bool a = idx < 4 ? (actAll[idx < 4 ? idx : 0] & 1u) : ((armAll >> (idx - 4)) & 1u);
+                if (a) llist[nl++] = (unsigned char)idx;
+            }
+#pragma unroll 1
+            for (int t = 0; t < 27; t++) {
+                const int o = c_seq_owner[t], ri = c_seq_row[t];
+                const unsigned a = o == 0 ? actAll[0] : (o == 1 ? actAll[1] : (o == 2 ? actAll[2] : actAll[3]));
+                if ((a >> ri) & 1u) clist[nc++] = (unsigned char)t;
+            }
+        }
         bool running = true;
         for (int it = 0; it < iters && running; it++) {
             float resid = 0.f;
-            constexpr int NLIM = ARM ? 4 + ARM_NJ : 4;       // limit rows in joint order: 4 leg rows (one per lane), then the arm
 #pragma unroll 1
-            for (int t = 0; t < NLIM + 27; t++) {
+            for (int tt = 0; tt < nl + nc; tt++) {
                 int o, ri;
-                if (t < NLIM) {                                     // limit rows: direction alternates per iteration
-                    const int idx = (it & 1) ? t : NLIM - 1 - t;
+                if (tt < nl) {                                      // limit rows: direction alternates per iteration
+                    const int idx = llist[(it & 1) ? tt : nl - 1 - tt];
                     if (ARM && idx >= 4) {                          // an arm joint-limit row, owned by lane 0
                         const int j = idx - 4;
                         float rsumA = armSg[j] * epsA[j] - (gA_[j][0] * beta.a.x + gA_[j][1] * beta.a.y + gA_[j][2] * beta.a.z + gA_[j][3] * beta.l.x + gA_[j][4] * beta.l.y + gA_[j][5] * beta.l.z);
@@ -709,7 +729,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                     }
                     o = idx; ri = 0;
                 }
-                else { o = c_seq_owner[t - NLIM]; ri = c_seq_row[t - NLIM]; }
+                else { const int t = clist[tt - nl]; o = c_seq_owner[t]; ri = c_seq_row[t]; }
                 const int ph = (ri == 0) ? 0 : (ri - 1) % 3;            // 0: unilateral row, 1/2: friction row
                 float rsum = Jq_[ri][0] * eps0 + Jq_[ri][1] * eps1 + Jq_[ri][2] * eps2
                            - (g_[ri][0] * beta.a.x + g_[ri][1] * beta.a.y + g_[ri][2] * beta.a.z + g_[ri][3] * beta.l.x + g_[ri][4] * beta.l.y + g_[ri][5] * beta.l.z);

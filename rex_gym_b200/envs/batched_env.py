@@ -140,14 +140,19 @@ class BatchedRexEnv(object):
         self.action_dim = self._L.rexsim_action_dim(c.task, c.signal)
         N, O, A = self.num_envs, self.obs_dim, self.action_dim
         dev = self.device
-        self._obs = torch.zeros((N, O), dtype=torch.float32, device=dev)
-        self._reward = torch.zeros((N,), dtype=torch.float32, device=dev)
-        self._done = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        # obs | reward | done live in ONE device allocation mirrored by ONE pinned host block, so the host path of
+        # step() is one H2D copy (actions) and one D2H copy (all results) per step
+        nb_obs, nb_rew = N * O * 4, N * 4
+        self._out = torch.zeros((nb_obs + nb_rew + ((N + 3) // 4) * 4,), dtype=torch.uint8, device=dev)
+        self._obs = self._out[:nb_obs].view(torch.float32).view(N, O)
+        self._reward = self._out[nb_obs:nb_obs + nb_rew].view(torch.float32)
+        self._done = self._out[nb_obs + nb_rew:nb_obs + nb_rew + N]
         self._act = torch.zeros((N, A), dtype=torch.float32, device=dev)
         self._h_act = torch.zeros((N, A), dtype=torch.float32).pin_memory()
-        self._h_obs = torch.zeros((N, O), dtype=torch.float32).pin_memory()
-        self._h_reward = torch.zeros((N,), dtype=torch.float32).pin_memory()
-        self._h_done = torch.zeros((N,), dtype=torch.uint8).pin_memory()
+        self._h_out = torch.zeros_like(self._out, device="cpu").pin_memory()
+        self._h_obs = self._h_out[:nb_obs].view(torch.float32).view(N, O)
+        self._h_reward = self._h_out[nb_obs:nb_obs + nb_rew].view(torch.float32)
+        self._h_done = self._h_out[nb_obs + nb_rew:nb_obs + nb_rew + N]
         self._h_err = torch.zeros((1,), dtype=torch.int32).pin_memory()
         p = C.c_void_p()
         _capi.check(self._L.rexsim_error_flags(self._h, C.byref(p)))
@@ -208,9 +213,7 @@ class BatchedRexEnv(object):
                                             self._done.data_ptr(), self._stream()))
             if on_device:
                 return self._obs, self._reward, self._done.bool(), _Info(self)
-            self._h_obs.copy_(self._obs, non_blocking=True)
-            self._h_reward.copy_(self._reward, non_blocking=True)
-            self._h_done.copy_(self._done, non_blocking=True)
+            self._h_out.copy_(self._out, non_blocking=True)
             self._h_err.copy_(self._err[N:N + 1], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         if int(self._h_err[0]) & ERR_NONFINITE:
