@@ -56,8 +56,8 @@ enum {
 
 #define REXSIM_MAX_TOE_PTS 32
 /* float offsets inside the model table (see rex_gym_b200/model_tables.py for the packer) */
-#define REXSIM_MT_BASE 0            /* mass, com[3], inertia[6](xx,yy,zz,xy,xz,yz), root_mass, root_inertia[3], pad[2] */
-#define REXSIM_MT_LEG 16            /* [4 legs][3 bodies][16]: jpos[3], mass, com[3], lower, inertia[6], upper, pad */
+#define REXSIM_MT_BASE 0            /* mass, com[3], inertia[6](xx,yy,zz,xy,xz,yz), root_mass, root_inertia[3], diag flag, pad */
+#define REXSIM_MT_LEG 16            /* [4 legs][3 bodies][16]: jpos[3], mass, com[3], lower, inertia[6], upper, diag flag */
 #define REXSIM_MT_TOE (16 + 192)    /* [4 legs][REXSIM_MAX_TOE_PTS][3] toe hull sample points, foot-body frame */
 #define REXSIM_MT_BOX (16 + 192 + 384)         /* [4 legs][3 bodies][8 corners][3] collision box corners, body frame */
 #define REXSIM_MT_BASEBOX (16 + 192 + 384 + 288) /* [3 boxes][8][3] base + chassis boxes */

@@ -8,17 +8,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librexsim.so")
 SOURCES = ["rexsim_kernel.cu", "rexsim_capi.cu"]
-HEADERS = ["rexsim_kernel.cuh", os.path.join("..", "..", "include", "rexsim.h")]
+HEADERS = ["rexsim_kernel.cuh", "rexsim_arm.cuh", os.path.join("..", "..", "include", "rexsim.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+STAMP = os.path.join(HERE, "librexsim.srchash")
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """Content-based (not mtime-based: snapshots copied to the GPU box do not have to preserve mtimes)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP).read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -32,6 +44,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building librexsim.so")
     if verbose:
         print(r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return LIB
 
 

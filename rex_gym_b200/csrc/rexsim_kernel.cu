@@ -90,7 +90,7 @@ __device__ __forceinline__ Sym6 pack(const AI& I) {
     return s;
 }
 __device__ __forceinline__ Sym6 spd_inverse(const Sym6& A) {
-    float L[21];
+    float L[21], invd[6];      // invd[j] = 1 / L[j][j]: every division of the factorisation becomes a multiply
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         float s = A.m[ix(j, j)];
@@ -100,6 +100,7 @@ __device__ __forceinline__ Sym6 spd_inverse(const Sym6& A) {
         // one Newton step keeps the factor at full fp32 accuracy
         inv = inv * (1.5f - 0.5f * s * inv * inv);
         L[ix(j, j)] = s * inv;
+        invd[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
             float t = A.m[ix(i, j)];
@@ -112,13 +113,13 @@ __device__ __forceinline__ Sym6 spd_inverse(const Sym6& A) {
     float Li[21];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-        Li[ix(j, j)] = 1.0f / L[ix(j, j)];
+        Li[ix(j, j)] = invd[j];
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
             float t = 0.f;
 #pragma unroll
             for (int k = j; k < i; k++) t = fmaf(-L[ix(i, k)], Li[ix(k, j)], t);
-            Li[ix(i, j)] = t / L[ix(i, i)];
+            Li[ix(i, j)] = t * invd[i];
         }
     }
     Sym6 R;   // A^-1 = Li^T Li
@@ -216,9 +217,10 @@ __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, floa
     const float V = 32.0f, R = 0.186f, Kt = 0.0954f;
     float pwm = -1.f * kp * (q - cmd) - kd * qd;
     pwm = fminf(fmaxf(pwm, -1.f), 1.f);
-    tau_obs = fminf(fmaxf(Kt * (pwm * V / R), -5.7f), 5.7f);
+    const float VoR = V / R, invR = 1.0f / R;     // compile-time constants: the per-motor divisions become multiplies
+    tau_obs = fminf(fmaxf(Kt * (pwm * VoR), -5.7f), 5.7f);
     float vnet = fminf(fmaxf(pwm * V - Kt * qd, -50.f), 50.f);
-    float cur = vnet / R;
+    float cur = vnet * invR;
     float mag = fabsf(cur), t;
     // np.interp over [0,10,...,60] -> [0,1,1.9,2.45,3.0,3.25,3.5]
     if (mag >= 60.f) t = 3.5f;
@@ -238,6 +240,7 @@ template <int TERRAIN, bool ARM>
 __device__ __forceinline__ void physics_substep(const Params& P, const float* __restrict__ sm, Lane& L, int leg,
                                                 const float* tau, Ground& G, Arm& AR, const float* tauA) {
     const float dt = (float)P.cfg.sim_dt_d;
+    const float inv_dt = 1.0f / dt;
     const float* LB = sm + REXSIM_MT_LEG + leg * 48;
     // ---- forward kinematics, world-aligned frame with origin at the base position -------------------
     M3 R0 = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
@@ -263,21 +266,21 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     {
         float m = LB[3]; V3 cw = p1 + mul(R1, mk(LB[4], LB[5], LB[6]));
         S3 Ib = {LB[8], LB[9], LB[10], LB[11], LB[12], LB[13]};
-        IA1 = rigid_inertia(m, cw, rotate_inertia(R1, Ib));
+        IA1 = rigid_inertia(m, cw, (LB[15] != 0.f ? rotate_inertia_diag(R1, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R1, Ib)));
         pA1 = crf(v1, mul(IA1, v1));
         pA1.a = pA1.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA1.l.z -= m * gz;
     }
     {
         float m = LB[16 + 3]; V3 cw = p2 + mul(R2, mk(LB[16 + 4], LB[16 + 5], LB[16 + 6]));
         S3 Ib = {LB[16 + 8], LB[16 + 9], LB[16 + 10], LB[16 + 11], LB[16 + 12], LB[16 + 13]};
-        IA2 = rigid_inertia(m, cw, rotate_inertia(R2, Ib));
+        IA2 = rigid_inertia(m, cw, (LB[16 + 15] != 0.f ? rotate_inertia_diag(R2, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R2, Ib)));
         pA2 = crf(v2, mul(IA2, v2));
         pA2.a = pA2.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA2.l.z -= m * gz;
     }
     {
         float m = LB[32 + 3]; V3 cw = p3 + mul(R3, mk(LB[32 + 4], LB[32 + 5], LB[32 + 6]));
         S3 Ib = {LB[32 + 8], LB[32 + 9], LB[32 + 10], LB[32 + 11], LB[32 + 12], LB[32 + 13]};
-        IA3 = rigid_inertia(m, cw, rotate_inertia(R3, Ib));
+        IA3 = rigid_inertia(m, cw, (LB[32 + 15] != 0.f ? rotate_inertia_diag(R3, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R3, Ib)));
         pA3 = crf(v3, mul(IA3, v3));
         pA3.a = pA3.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA3.l.z -= m * gz;
     }
@@ -304,7 +307,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         const float* B = sm + REXSIM_MT_BASE;
         float m = B[0]; V3 cw = mul(R0, mk(B[1], B[2], B[3]));
         S3 Ib = {B[4], B[5], B[6], B[7], B[8], B[9]};
-        IA0 = rigid_inertia(m, cw, rotate_inertia(R0, Ib));
+        IA0 = rigid_inertia(m, cw, B[14] != 0.f ? rotate_inertia_diag(R0, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R0, Ib));
         pA0 = crf(v0, mul(IA0, v0));
         pA0.a = pA0.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA0.l.z -= m * gz;
         // Bullet default base damping 0.04 (K1 = K2) with the un-merged root link's mass / inertia
@@ -535,7 +538,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             const float slop = 1e-5f;
             float pen = best + slop;
             float poserr = 0.f, velerr = -relv[0];
-            if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.cfg.erp_contact / dt;
+            if (pen > 0.f) velerr -= pen * inv_dt; else poserr = -pen * P.cfg.erp_contact * inv_dt;
             rhs[0] = (pen > -0.04f) ? (poserr + velerr) * dinv[0] : velerr * dinv[0];
             rhs[1] = -relv[1] * dinv[1];
             rhs[2] = -relv[2] * dinv[2];
@@ -648,7 +651,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 if (d == 0) {
                     float pen = dist + 1e-5f;
                     float poserr = 0.f, velerr = -relv;
-                    if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.cfg.erp_contact / dt;
+                    if (pen > 0.f) velerr -= pen * inv_dt; else poserr = -pen * P.cfg.erp_contact * inv_dt;
                     rhs_[r0] = (pen > -0.04f) ? (poserr + velerr) * dinv_[r0] : velerr * dinv_[r0];
                 } else rhs_[r0 + d] = -relv * dinv_[r0 + d];
             }
@@ -657,7 +660,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             SV z; z.a = mk(0, 0, 0); z.l = mk(0, 0, 0);
             float relv = setup_row(0, z, limJ == 0 ? limSg : 0.f, limJ == 1 ? limSg : 0.f, limJ == 2 ? limSg : 0.f);
             float erp = (limPen > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
-            rhs_[0] = (-limPen * erp / dt - relv) * dinv_[0];
+            rhs_[0] = (-limPen * erp * inv_dt - relv) * dinv_[0];
         }
         if (activeB) setup_contact(1, rcB, nrmB, 0, bestB);
         if (activeU) setup_contact(4, rcU, nrmU, kU, bestU);
@@ -679,7 +682,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 denA_[j] = dn; dinvA_[j] = 1.0f / dn;
                 float relv = armSg[j] * AR.qs[j];
                 float erp = (armPen[j] > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
-                rhsA_[j] = (-armPen[j] * erp / dt - relv) * dinvA_[j];
+                rhsA_[j] = (-armPen[j] * erp * inv_dt - relv) * dinvA_[j];
             }
         }
         SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);

@@ -130,6 +130,18 @@ __device__ __forceinline__ S3 rotate_inertia(const M3& R, const S3& I) {
     o.xy = dot(r0, i1); o.xz = dot(r0, i2); o.yz = dot(r1, i2);
     return o;
 }
+// R * diag(d) * R^T for a body whose inertia tensor is diagonal in its own frame (every Rex box link)
+__device__ __forceinline__ S3 rotate_inertia_diag(const M3& R, float dx, float dy, float dz) {
+    V3 a = dx * R.c0, b = dy * R.c1, c = dz * R.c2;
+    S3 o;
+    o.xx = fmaf(a.x, R.c0.x, fmaf(b.x, R.c1.x, c.x * R.c2.x));
+    o.yy = fmaf(a.y, R.c0.y, fmaf(b.y, R.c1.y, c.y * R.c2.y));
+    o.zz = fmaf(a.z, R.c0.z, fmaf(b.z, R.c1.z, c.z * R.c2.z));
+    o.xy = fmaf(a.x, R.c0.y, fmaf(b.x, R.c1.y, c.x * R.c2.y));
+    o.xz = fmaf(a.x, R.c0.z, fmaf(b.x, R.c1.z, c.x * R.c2.z));
+    o.yz = fmaf(a.y, R.c0.z, fmaf(b.y, R.c1.z, c.y * R.c2.z));
+    return o;
+}
 // spatial cross products
 __device__ __forceinline__ SV crm(SV v, SV m) { SV r; r.a = cross(v.a, m.a); r.l = cross(v.a, m.l) + cross(v.l, m.a); return r; }
 __device__ __forceinline__ SV crf(SV v, SV f) { SV r; r.a = cross(v.a, f.a) + cross(v.l, f.l); r.l = cross(v.a, f.l); return r; }

@@ -22,6 +22,11 @@ def _rpy_to_mat(rpy):
     return rz @ ry @ rx          # URDF fixed-axis roll, pitch, yaw
 
 
+def _is_diag(I):
+    I = np.asarray(I, dtype=np.float64)
+    return bool(np.all(I[~np.eye(3, dtype=bool)] == 0.0))
+
+
 def _sym6(I):
     I = np.asarray(I, dtype=np.float64)
     return [I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]]
@@ -49,6 +54,7 @@ def pack_model_tables(mark="base"):
     t[MT_BASE + 4:MT_BASE + 10] = _sym6(b0["inertia"])
     t[MT_BASE + 10] = j["root_mass"]
     t[MT_BASE + 11:MT_BASE + 14] = j["root_inertia"]
+    t[MT_BASE + 14] = 1.0 if _is_diag(b0["inertia"]) else 0.0       # flag: inertia tensor diagonal in the body frame
     boxes = [s for s in b0["shapes"] if s["kind"] == "box"]
     if len(boxes) != 3:
         raise ValueError("expected base + 2 chassis collision boxes")
@@ -70,6 +76,7 @@ def pack_model_tables(mark="base"):
             t[o + 7] = b["lower"]
             t[o + 8:o + 14] = _sym6(b["inertia"])
             t[o + 14] = b["upper"]
+            t[o + 15] = 1.0 if _is_diag(b["inertia"]) else 0.0
             box = [s for s in b["shapes"] if s["kind"] == "box"]
             if len(box) != 1:
                 raise ValueError("expected one collision box per leg body")

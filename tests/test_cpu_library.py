@@ -95,6 +95,8 @@ def test_reference_surface_names():
         assert hasattr(R.BatchedRexEnv, m)
     with pytest.raises(ValueError):
         R.make("RexGo-v0")
+    from rex_gym_b200.envs.gym import walk_env, gallop_env, turn_env, standup_env     # the reference's module paths
+    assert walk_env.RexWalkEnv and gallop_env.RexReactiveEnv and turn_env.RexTurnEnv and standup_env.RexStandupEnv
 
 
 def test_terrain_bank_follows_the_reference_stream():
