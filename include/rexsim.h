@@ -42,7 +42,8 @@ typedef enum {
     REXSIM_ERR_UNSUPPORTED = -4,  /* valid reference configuration not built yet */
 } RexSimStatus;
 
-enum { REXSIM_TASK_WALK = 0, REXSIM_TASK_GALLOP = 1, REXSIM_TASK_TURN = 2, REXSIM_TASK_STANDUP = 3 };
+enum { REXSIM_TASK_WALK = 0, REXSIM_TASK_GALLOP = 1, REXSIM_TASK_TURN = 2, REXSIM_TASK_STANDUP = 3,
+       REXSIM_TASK_POSES = 4 /* RexPosesEnv, rex_gym/envs/gym/poses_env.py:21 */ };
 enum { REXSIM_SIGNAL_IK = 0, REXSIM_SIGNAL_OL = 1 };
 enum { REXSIM_TERRAIN_PLANE = 0, REXSIM_TERRAIN_RANDOM = 1 };
 
@@ -92,6 +93,8 @@ typedef struct {
     int32_t toe_npts;                 /* valid points per toe in the model table */
     float toe_margin;
     int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */
+    float pose_values[5];             /* poses task: base_y, base_z, base_roll, base_pitch, base_yaw constructor arguments
+                                       * (poses_env.py:49-53); all NaN = None: the pose rotates per reset, target drawn in range */
 } RexSimConfig;
 
 typedef struct RexSim RexSim;
@@ -109,6 +112,12 @@ void rexsim_destroy(RexSim* sim);
 
 /* actions dev [N][A] f32; obs dev [N][O] f32; reward dev [N] f32; done dev [N] u8 */
 int rexsim_step(RexSim* sim, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
+/* Host-buffer form of rexsim_step -- BatchEnv.step with numpy arrays (batch_env.py:63-90): h_actions HOST [N][A] f32,
+ * h_out HOST block of rexsim_host_out_bytes() bytes laid out as obs [N][O] f32 | reward [N] f32 | done [N] u8 | pad to 4 |
+ * int32 OR of all error flags.  One call = H2D copy of the actions, the step kernel, one D2H copy of the results (+4 bytes of
+ * flags) on `stream`, then a wait for that stream.  Pinned (page-locked) host memory gives the full copy speed. */
+int64_t rexsim_host_out_bytes(const RexSim* sim);
+int rexsim_step_host(RexSim* sim, const float* h_actions, void* h_out, void* stream);
 /* idx dev [k] int32 (NULL: all envs, k ignored); obs_out dev [k][O] or NULL */
 int rexsim_reset(RexSim* sim, const int32_t* idx, int32_t k, float* obs_out, void* stream);
 

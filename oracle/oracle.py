@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MODEL_DIR = os.path.join(HERE, "..", "rex_gym_b200", "model")
 
 MAXB, MAXDOF, MAXSHAPE, MAXPTS = 20, 18, 40, 400
-TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3}
+TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3, "poses": 4}
 SIGNALS = {"ik": 0, "ol": 1}
 TERRAINS = {"plane": 0, "random": 1}
 
@@ -46,7 +46,7 @@ class RexoConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("seed", C.c_uint64),
         ("nfields", C.c_int32), ("fields", C.POINTER(C.c_float)), ("friction", C.c_double),
         ("residual_threshold", C.c_double), ("erp_contact", C.c_double), ("erp_joint", C.c_double),
-        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32),
+        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("pose_values", C.c_double * 5),
     ]
 
 
@@ -64,6 +64,7 @@ class RexoEnv(C.Structure):
         ("reset_count", C.c_uint32), ("field_id", C.c_int32),
         ("contact_mask", C.c_int32), ("contact_vertex", C.c_int32 * MAXSHAPE),
         ("solver_iters", C.c_int32), ("limit_rows", C.c_int32),
+        ("next_pose", C.c_int32), ("target_value", C.c_double),
     ]
 
 
@@ -188,14 +189,15 @@ class OracleSim:
                  kp_range=None, kd_range=None, target_position=None, backwards=None,
                  target_orient=None, init_orient=None, energy_weight=None, normalize=False,
                  max_episode_steps=0, seed=1234, nfields=0, fields=None, toes_only=False, settle=True,
-                 solver_iterations=None, residual_threshold=1e-7, env_offset=0):
+                 solver_iterations=None, residual_threshold=1e-7, env_offset=0,
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None):
         self.L = lib(f32)
         self.model, self.model_json = load_model(mark, toes_only=toes_only)
         c = RexoConfig()
         c.num_envs = num_envs
         c.task, c.signal, c.terrain = TASKS[task], SIGNALS[signal], TERRAINS[terrain]
-        rep = action_repeat or (6 if task == "gallop" else 5)
-        cts = control_time_step or (0.006 if task == "gallop" else 0.005)
+        rep = action_repeat or (6 if task in ("gallop", "poses") else 5)
+        cts = control_time_step or (0.006 if task in ("gallop", "poses") else 0.005)
         c.action_repeat = rep
         c.sim_dt = cts / rep
         c.solver_iterations = solver_iterations or int(300 / rep)
@@ -223,6 +225,8 @@ class OracleSim:
         c.erp_contact, c.erp_joint = 0.08, 0.2
         c.settle_on_reset = int(settle)
         c.env_offset = int(env_offset)
+        for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):
+            c.pose_values[k] = float("nan") if v is None else float(v)
         self.cfg = c
         self.h = self.L.rexo_create(C.byref(self.model), C.byref(c))
         self.N = num_envs

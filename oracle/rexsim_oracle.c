@@ -831,11 +831,27 @@ static void standup_command(RexoSim* s, RexoEnv* e, const double* action, double
     for (int i = 0; i < 12; i++) cmd[i] = POSE_STAND[i] * ((.1 + action[0]) / t + 1.5);
 }
 
+/* RexPosesEnv._signal: poses_env.py:187-225 (ramp :178-185; Kinematics.solve on the staged base pose) */
+static const double POSE_RANGE[5][2] = {{-0.007, 0.007}, {-0.048, 0.021}, {-PI / 4, PI / 4}, {-PI / 4, PI / 4}, {-PI / 4, PI / 4}};  /* rex_gym_env.py:260-267 */
+static void poses_command(RexoSim* s, RexoEnv* e, const double* action, double* cmd) {
+    static const double FRAMES[12] = {0.115, -0.0925, -0.2, 0.115, 0.0925, -0.2, -0.115, -0.0925, -0.2, -0.115, 0.0925, -0.2};
+    double t = e->step_counter * s->c.sim_dt;
+    double p = 0.8 + action[0], end_t = 0.0;
+    double coeff = (end_t <= t && t <= p + end_t) ? t : 1.0;
+    double staged = e->target_value * coeff;
+    double pos[3] = {0.01, 0, 0}, rpy[3] = {0, 0, 0}, ang[12];       /* _ranges defaults: base_x 0.01, others 0 */
+    if (e->next_pose == 0) pos[1] = staged; else if (e->next_pose == 1) pos[2] = staged;
+    else rpy[e->next_pose - 2] = staged;
+    rexo_ik_solve(rpy, pos, FRAMES, ang);
+    for (int k = 0; k < 3; k++) { cmd[k] = ang[3 + k]; cmd[3 + k] = ang[k]; cmd[6 + k] = ang[9 + k]; cmd[9 + k] = ang[6 + k]; }   /* :209-214 */
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* reward / termination / observation                                                           */
 /* ------------------------------------------------------------------------------------------- */
 static double env_reward(RexoSim* s, RexoEnv* e) {
     const RexoConfig* c = &s->c;
+    if (c->task == REXO_TASK_POSES) return 1.0;                                        /* poses_env.py:256-258 */
     if (c->task == REXO_TASK_TURN) return 0.035 - fabs(e->pos[0]) - fabs(e->pos[1]);   /* turn_env.py:362-367 */
     if (c->task == REXO_TASK_STANDUP) {                                                /* standup_env.py:151-167 */
         double pr = fabs(0.0 - e->pos[0]) + fabs(0.0 - e->pos[1]) + fabs(0.21 - e->pos[2]);
@@ -866,6 +882,7 @@ static double env_reward(RexoSim* s, RexoEnv* e) {
 static int env_done(RexoSim* s, RexoEnv* e) {
     const RexoConfig* c = &s->c;
     real q4[4] = {e->quat[0], e->quat[1], e->quat[2], e->quat[3]};
+    if (c->task == REXO_TASK_POSES) return e->env_goal_reached;      /* is_fallen -> False (poses_env.py:247-254) */
     if (c->task == REXO_TASK_WALK || c->task == REXO_TASK_TURN) {    /* walk_env.py:326-338, rex_gym_env.py:490-495 */
         real R[9]; quat_to_mat(q4, R);
         return (R[8] < 0.85) || e->env_goal_reached;
@@ -896,6 +913,7 @@ static void action_bounds(const RexoSim* s, int j, double* lo, double* hi) {
         case REXO_TASK_WALK: b = c->signal == REXO_SIGNAL_IK ? 0.4 : 0.01; *lo = -b; *hi = b; break;   /* walk_env.py:104-114 */
         case REXO_TASK_GALLOP: b = c->signal == REXO_SIGNAL_IK ? 0.4 : 0.3; *lo = b; *hi = -b; break;  /* inverted Box gallop_env.py:128-130 */
         case REXO_TASK_TURN: *lo = -0.01; *hi = 0.01; break;                                           /* turn_env.py:100-110 */
+        case REXO_TASK_POSES: *lo = -0.1; *hi = 0.1; break;                                            /* poses_env.py:118-120 */
         default: *lo = -0.1; *hi = 0.1; break;                                                         /* standup_env.py:99-101 */
     }
 }
@@ -923,7 +941,8 @@ static void settle_state(RexoSim* s, RexoEnv* e) {   /* Rex.Reset: rex.py:296-32
         e->overheat[i] = 0; e->enabled[i] = 1; e->tau_obs[i] = 0; e->cmd[i] = 0;
     }
     e->step_counter = 0;
-    if (s->c.settle_on_reset) {
+    /* RexPosesEnv.reset calls RexGymEnv.reset() with initial_motor_angles=None: no holding phase (rex.py:307) */
+    if (s->c.settle_on_reset && s->c.task != REXO_TASK_POSES) {
         for (int it = 0; it < 100; it++) apply_action_and_step(s, e, s->stand_pose);     /* :315-318 */
         int n2 = (int)(0.5 / s->c.sim_dt);                                               /* reset_duration=0.5 */
         for (int it = 0; it < n2; it++) apply_action_and_step(s, e, s->init_pose);       /* :319-323 */
@@ -974,6 +993,18 @@ static void reset_env(RexoSim* s, int i) {
         euler_to_quat(rpy, q4);                                  /* :157-159 */
         e->pos[0] = 0; e->pos[1] = 0; e->pos[2] = 0.21;
         for (int a = 0; a < 4; a++) e->quat[a] = q4[a];
+    } else if (c->task == REXO_TASK_POSES) {    /* poses_env.py:148-176 */
+        int any = 0;
+        for (int k = 0; k < 5; k++) any |= !isnan(c->pose_values[k]);
+        if (any) {                               /* fill_next_pose_and_target (a None argument counts as 0.0) */
+            e->next_pose = 4;
+            for (int k = 0; k < 4; k++) if (!isnan(c->pose_values[k]) && c->pose_values[k] != 0.0) { e->next_pose = k; break; }
+            double v = c->pose_values[e->next_pose];
+            e->target_value = isnan(v) ? 0.0 : v;
+        } else {                                 /* deque rotation: the constructor's own reset() consumed 'base_y' */
+            e->next_pose = (int)(rc % 5u);
+            e->target_value = rand_uniform(s, i, rc, 6, POSE_RANGE[e->next_pose][0], POSE_RANGE[e->next_pose][1]);
+        }
     }
 }
 
@@ -990,6 +1021,7 @@ RexoSim* rexo_create(const RexoModel* model, const RexoConfig* cfg) {
         case REXO_TASK_WALK: s->act_dim = cfg->signal == REXO_SIGNAL_IK ? 2 : 8; s->obs_dim = 4; break;
         case REXO_TASK_GALLOP: s->act_dim = cfg->signal == REXO_SIGNAL_IK ? 2 : 4; s->obs_dim = 4 + model->nmotor; break;
         case REXO_TASK_TURN: s->act_dim = 2; s->obs_dim = 4; break;
+        case REXO_TASK_POSES: s->act_dim = 1; s->obs_dim = 4; break;
         default: s->act_dim = 1; s->obs_dim = 4; break;
     }
     const double* ip = POSE_STAND;
@@ -1034,6 +1066,7 @@ static void transform_action(RexoSim* s, RexoEnv* e, const double* act, double* 
         case REXO_TASK_WALK: walk_command(s, e, a, cmd); break;
         case REXO_TASK_GALLOP: gallop_command(s, e, a, cmd); break;
         case REXO_TASK_TURN: turn_command(s, e, a, cmd); break;
+        case REXO_TASK_POSES: poses_command(s, e, a, cmd); break;
         default: standup_command(s, e, a, cmd); break;
     }
     for (int j = 12; j < s->m.nmotor; j++) cmd[j] = ARM_REST[j - 12];   /* rex_gym_env.py:363-367 */

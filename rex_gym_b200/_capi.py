@@ -22,11 +22,12 @@ class RexSimConfig(C.Structure):
         ("seed", C.c_uint64), ("nfields", C.c_int32), ("fields", C.c_void_p),
         ("friction", C.c_float), ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
         ("toe_npts", C.c_int32), ("toe_margin", C.c_float), ("env_offset", C.c_int32),
+        ("pose_values", C.c_float * 5),
     ]
 
 
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
-           "rexsim_step", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
+           "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
            "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
 
 _LIB = None
@@ -52,6 +53,9 @@ def load():
     L.rexsim_destroy.argtypes = [C.c_void_p]
     L.rexsim_destroy.restype = None
     L.rexsim_step.argtypes = [C.c_void_p] * 6
+    L.rexsim_step_host.argtypes = [C.c_void_p] * 4
+    L.rexsim_host_out_bytes.argtypes = [C.c_void_p]
+    L.rexsim_host_out_bytes.restype = C.c_int64
     L.rexsim_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.rexsim_get_state.argtypes = [C.c_void_p] * 4
     L.rexsim_set_state.argtypes = [C.c_void_p] * 3

@@ -38,7 +38,7 @@ __device__ __forceinline__ M3 axis_angle(V3 a, float q) {   // Rodrigues, column
 
 // ABA passes 1 and 2 over the arm: kinematics, bias terms, inward reduction.  Returns the arm's articulated inertia and
 // bias force as seen by the base (to be added to the base sums), fills A.S/U/k/u/cJ.
-__device__ __noinline__ void arm_inward(const float* __restrict__ AT, const M3& R0, SV v0, Arm& A, const float* tauA,
+static __device__ __noinline__ void arm_inward(const float* __restrict__ AT, const M3& R0, SV v0, Arm& A, const float* tauA,
                                         AI& IaOut, SV& paOut) {
     AI IAb[ARM_NJ]; SV pAb[ARM_NJ];
     M3 Rp = R0; V3 pp = mk(0.f, 0.f, 0.f); SV vp = v0;
@@ -76,7 +76,7 @@ __device__ __noinline__ void arm_inward(const float* __restrict__ AT, const M3& 
     }
 }
 // ABA pass 3: joint accelerations -> unconstrained joint rates A.qs
-__device__ __noinline__ void arm_outward(Arm& A, SV a0, float dt) {
+static __device__ __noinline__ void arm_outward(Arm& A, SV a0, float dt) {
     SV a = a0;
 #pragma unroll 1
     for (int j = 0; j < ARM_NJ; j++) {
@@ -87,7 +87,7 @@ __device__ __noinline__ void arm_outward(Arm& A, SV a0, float dt) {
     }
 }
 // response of the arm joints to a base velocity change b plus accumulated joint impulses us[] (fixed-base part)
-__device__ __noinline__ void arm_apply(Arm& A, SV b, const float* us, float* dq) {
+static __device__ __noinline__ void arm_apply(Arm& A, SV b, const float* us, float* dq) {
 #pragma unroll 1
     for (int j = 0; j < ARM_NJ; j++) {
         dq[j] = (us[j] - sdot(ld6(A.U[j]), b)) * A.k[j];
@@ -96,7 +96,7 @@ __device__ __noinline__ void arm_apply(Arm& A, SV b, const float* us, float* dq)
 }
 // one joint-limit row of the arm (unit generalized force sg on joint jl): base bias g, fixed-base joint response ee[],
 // inward joint terms uu[]
-__device__ __noinline__ void arm_row(const Arm& A, int jl, float sg, SV& g, float* ee, float* uu) {
+static __device__ __noinline__ void arm_row(const Arm& A, int jl, float sg, SV& g, float* ee, float* uu) {
     SV pD; pD.a = mk(0, 0, 0); pD.l = mk(0, 0, 0);
 #pragma unroll 1
     for (int j = ARM_NJ - 1; j >= 0; j--) {

@@ -25,6 +25,9 @@ struct RexSim {
     float* d_zoff = nullptr;
     int32_t* d_err = nullptr;
     float* d_cmd = nullptr;
+    float* d_act = nullptr;            // staging for rexsim_step_host
+    uint8_t* d_out = nullptr;          // obs | reward | done (same layout as the host block)
+    int A = 0, O = 0;
     int nsnap = 1;
     int64_t launches = 0;
 };
@@ -47,7 +50,7 @@ int rexsim_action_dim(int32_t task, int32_t signal) {
         case REXSIM_TASK_WALK: return signal == REXSIM_SIGNAL_IK ? 2 : 8;     /* walk_env.py:108-113 */
         case REXSIM_TASK_GALLOP: return signal == REXSIM_SIGNAL_IK ? 2 : 4;   /* gallop_env.py:123-127 */
         case REXSIM_TASK_TURN: return 2;                                      /* turn_env.py:104-108 */
-        default: return 1;                                                    /* standup_env.py:99 */
+        default: return 1;                                                    /* standup_env.py:99, poses_env.py:118 */
     }
 }
 int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int) {
@@ -59,7 +62,7 @@ int rexsim_state_words(const RexSimConfig* cfg, int32_t* n_float, int32_t* n_int
 
 static int validate(const RexSimConfig* c) {
     if (c->num_envs <= 0) return fail(REXSIM_ERR_INVALID, "num_envs must be positive");
-    if (c->task < 0 || c->task > 3 || c->signal < 0 || c->signal > 1) return fail(REXSIM_ERR_INVALID, "bad task/signal");
+    if (c->task < 0 || c->task > 4 || c->signal < 0 || c->signal > 1) return fail(REXSIM_ERR_INVALID, "bad task/signal");
     if (c->num_motors != 12 && c->num_motors != 18) return fail(REXSIM_ERR_INVALID, "num_motors must be 12 (base) or 18 (arm)");
     if (c->num_motors == 18 && !(c->task == REXSIM_TASK_STANDUP || (c->task == REXSIM_TASK_WALK && c->signal == REXSIM_SIGNAL_IK)))
         return fail(REXSIM_ERR_UNSUPPORTED, "mark='arm' is built for the standup and walk-ik tasks");
@@ -103,6 +106,10 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     CK(cudaMemset(s->d_err, 0, (size_t)(N + 1) * sizeof(int32_t)));
     CK(cudaMalloc(&s->d_cmd, (size_t)12 * N * sizeof(float)));
     CK(cudaMemset(s->d_cmd, 0, (size_t)12 * N * sizeof(float)));
+    s->A = rexsim_action_dim(cfg->task, cfg->signal); s->O = rexsim_obs_dim(cfg->task, cfg->num_motors);
+    CK(cudaMalloc(&s->d_act, (size_t)N * s->A * sizeof(float)));
+    CK(cudaMalloc(&s->d_out, (size_t)rexsim_host_out_bytes(s)));
+    CK(cudaMemset(s->d_out, 0, (size_t)rexsim_host_out_bytes(s)));
     if (cfg->terrain == REXSIM_TERRAIN_RANDOM) {
         // vertical centring of each field: btHeightfieldTerrainShape local origin = (min+max)/2
         std::vector<float> h((size_t)65536), zo(cfg->nfields);
@@ -133,7 +140,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
 void rexsim_destroy(RexSim* s) {
     if (!s) return;
     cudaFree(s->d_model); cudaFree(s->d_sf); cudaFree(s->d_si); cudaFree(s->d_snap_f); cudaFree(s->d_snap_i);
-    cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd);
+    cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd); cudaFree(s->d_act); cudaFree(s->d_out);
     delete s;
 }
 
@@ -144,6 +151,29 @@ int rexsim_step(RexSim* s, const float* actions, float* obs, float* reward, uint
     cudaError_t e = launch_step(P, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "step launch");
     s->launches++;
+    return REXSIM_OK;
+}
+
+static size_t out_done_offset(const RexSim* s) { return ((size_t)s->P.N * s->O + s->P.N) * sizeof(float); }
+static size_t out_err_offset(const RexSim* s) { return (out_done_offset(s) + (size_t)s->P.N + 3) & ~(size_t)3; }
+int64_t rexsim_host_out_bytes(const RexSim* s) {
+    if (!s) return 0;
+    return (int64_t)(out_err_offset(s) + sizeof(int32_t));
+}
+int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* stream) {
+    if (!s || !h_actions || !h_out) return fail(REXSIM_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = s->P.N;
+    CK(cudaMemcpyAsync(s->d_act, h_actions, N * s->A * sizeof(float), cudaMemcpyHostToDevice, st));
+    Params P = s->P;
+    P.actions = s->d_act;
+    P.obs = (float*)s->d_out; P.reward = (float*)s->d_out + N * s->O; P.done = s->d_out + out_done_offset(s);
+    cudaError_t e = launch_step(P, st);
+    if (e != cudaSuccess) return cuda_fail(e, "step launch");
+    s->launches++;
+    CK(cudaMemcpyAsync(h_out, s->d_out, out_err_offset(s), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char*)h_out + out_err_offset(s), s->d_err + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return REXSIM_OK;
 }
 

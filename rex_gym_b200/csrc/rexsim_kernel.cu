@@ -209,8 +209,8 @@ __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {   // btPlaneSp
 }
 
 // generic-path Gauss-Seidel order after the 4 limit rows: normals (base, then per leg upper, foot), then frictions
-__constant__ int c_seq_owner[27] = {0, 0, 0, 1, 1, 2, 2, 3, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3};
-__constant__ int c_seq_row[27] = {1, 4, 7, 4, 7, 4, 7, 4, 7, 2, 3, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9};
+static __constant__ int c_seq_owner[27] = {0, 0, 0, 1, 1, 2, 2, 3, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3};
+static __constant__ int c_seq_row[27] = {1, 4, 7, 4, 7, 4, 7, 4, 7, 2, 3, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9};
 
 // motor model + overheat (rex_gym/model/motor.py:76-143, rex_gym/model/rex.py:601-623) for one joint
 __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, float kp, float kd, float& tau_obs) {
@@ -789,7 +789,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
 }
 
 // Rex.ApplyAction + stepSimulation (rex_gym/model/rex.py:158-163,568-641) for the own leg's three motors
-__constant__ float c_arm_rest[6] = {-1.6f, -1.6f, 0.f, 0.f, 1.6f, 0.f};   // ARM_POSES['rest'] rex_constants.py:3-8
+static __constant__ float c_arm_rest[6] = {-1.6f, -1.6f, 0.f, 0.f, 1.6f, 0.f};   // ARM_POSES['rest'] rex_constants.py:3-8
 
 template <int TERRAIN, bool ARM>
 __device__ __forceinline__ void apply_action_and_step(const Params& P, const float* sm, Lane& L, int leg,
@@ -870,6 +870,27 @@ __device__ __forceinline__ void solve_ik_leg(V3 c, bool right, float* ang) {
     ang[0] = theta; ang[1] = -alpha; ang[2] = -gamma;
 }
 
+// Kinematics.transform (kinematics.py:49-78): R(rpy) * (v + pos), R = Rx*Ry*Rz (identity when rpy == 0)
+__device__ __forceinline__ V3 ik_transform(V3 v, V3 rpy, V3 pos) {
+    V3 t = v + pos;
+    if (rpy.x != 0.f || rpy.y != 0.f || rpy.z != 0.f) {
+        float sx, cx, sy, cy, sz, cz;
+        sincosf(rpy.x, &sx, &cx); sincosf(rpy.y, &sy, &cy); sincosf(rpy.z, &sz, &cz);
+        V3 a = mk(cz * t.x - sz * t.y, sz * t.x + cz * t.y, t.z);
+        V3 b = mk(cy * a.x + sy * a.z, a.y, -sy * a.x + cy * a.z);
+        t = mk(b.x, cx * b.y - sx * b.z, sx * b.y + cx * b.z);
+    }
+    return t;
+}
+// Kinematics.solve for the own leg with a general base pose (kinematics.py:104-142); il = IK leg index (FR,FL,RR,RL)
+__device__ __forceinline__ void solve_ik_pose(V3 rpy, V3 pos, V3 frame, int il, float* ang) {
+    V3 hip = mk((il < 2) ? 0.115f : -0.115f, (il & 1) ? 0.0375f : -0.0375f, 0.f);
+    V3 hv = ik_transform(hip, rpy, pos);
+    V3 c = frame - hv;
+    V3 tc = ik_transform(c, mk(-rpy.x, -rpy.y, -rpy.z), mk(-pos.x, -pos.y, -pos.z));
+    solve_ik_leg(tc, (il & 1) == 0, ang);
+}
+
 struct GaitState { double phi; int last_step; float alpha; };
 
 // GaitPlanner.loop + Kinematics.solve for the own leg; il = IK leg index (FR,FL,RR,RL) = lane ^ 1
@@ -919,8 +940,8 @@ __device__ __forceinline__ void ik_signal(GaitState& G, bool gallop, int step_co
     solve_ik_leg(tc, (il & 1) == 0, cmd);
 }
 
-__constant__ float c_pose_stand[3] = {0.f, -0.88643435f, 1.30197369f};
-__constant__ float c_pose_stand_ol[3] = {0.15192765f, -0.90412283f, 1.48156545f};   // sign of [0] alternates per leg
+static __constant__ float c_pose_stand[3] = {0.f, -0.88643435f, 1.30197369f};
+static __constant__ float c_pose_stand_ol[3] = {0.15192765f, -0.90412283f, 1.48156545f};   // sign of [0] alternates per leg
 
 __device__ __forceinline__ void init_pose(int signal, int leg, float* p) {
     if (signal == REXSIM_SIGNAL_OL) { p[0] = (leg & 1) ? -c_pose_stand_ol[0] : c_pose_stand_ol[0]; p[1] = c_pose_stand_ol[1]; p[2] = c_pose_stand_ol[2]; }
@@ -1043,6 +1064,15 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
             float so[3]; init_pose(REXSIM_SIGNAL_OL, leg, so);
             cmd[0] = so[0] + o0; cmd[1] = so[1] + o1; cmd[2] = so[2] + o2;
         }
+    } else if (TASK == REXSIM_TASK_POSES) {                           // envs/gym/poses_env.py:178-225
+        const double p = 0.8 + (double)act[0];
+        const double coeff = (0.0 <= t && t <= p) ? t : 1.0;
+        const float staged = (float)((double)K.target * coeff);
+        const int pose = (K.flags >> FL_POSE_SHIFT) & 7;
+        V3 pos = mk(0.01f, pose == 0 ? staged : 0.f, pose == 1 ? staged : 0.f);
+        V3 rpy = mk(pose == 2 ? staged : 0.f, pose == 3 ? staged : 0.f, pose == 4 ? staged : 0.f);
+        const int il = leg ^ 1;
+        solve_ik_pose(rpy, pos, mk((il < 2) ? 0.115f : -0.115f, (il & 1) ? 0.0925f : -0.0925f, -0.2f), il, cmd);
     } else {                                                          // envs/gym/standup_env.py:113-134
         if (t > 0.1) { cmd[0] = c_pose_stand[0]; cmd[1] = c_pose_stand[1]; cmd[2] = c_pose_stand[2]; return; }
         double tt = t + 1;
@@ -1104,7 +1134,7 @@ __device__ __forceinline__ void store_lane(float* sf, int32_t* si, int N, int en
         sf[F_TARGET * (size_t)N + env] = K.target;
         si[I_STEP * (size_t)N + env] = K.step_counter;
         si[I_ENVSTEP * (size_t)N + env] = K.env_step;
-        si[I_FLAGS * (size_t)N + env] = (K.flags & ((1 << FL_ENABLED_SHIFT) - 1)) | (int32_t)(en << FL_ENABLED_SHIFT);
+        si[I_FLAGS * (size_t)N + env] = (K.flags & (((1 << FL_ENABLED_SHIFT) - 1) | (7 << FL_POSE_SHIFT))) | (int32_t)(en << FL_ENABLED_SHIFT);
         si[I_ENDSTEP * (size_t)N + env] = K.end_step;
         si[I_GPLAST * (size_t)N + env] = K.G.last_step;
         si[I_PHI_HI * (size_t)N + env] = __double2hiint(K.G.phi);
@@ -1167,6 +1197,23 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
         L.pos = mk(0.f, 0.f, 0.21f);
         float hy = (float)(io * 0.5);
         L.qx = 0.f; L.qy = 0.f; L.qz = sinf(hy); L.qw = cosf(hy);
+    } else if (c.task == REXSIM_TASK_POSES) {                         // poses_env.py:148-176
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 5; k++) any = any || !isnan(c.pose_values[k]);
+        int pose;
+        if (any) {                      // fill_next_pose_and_target (a None argument counts as 0.0)
+            pose = 4;
+#pragma unroll
+            for (int k = 3; k >= 0; k--) if (!isnan(c.pose_values[k]) && c.pose_values[k] != 0.f) pose = k;
+            float v = c.pose_values[pose];
+            K.target = isnan(v) ? 0.f : v;
+        } else {                        // deque rotation; the constructor's own reset() consumed 'base_y'
+            pose = (int)(rc % 5u);
+            const double lo = pose == 0 ? -0.007 : pose == 1 ? -0.048 : -PI_D / 4, hi = pose == 0 ? 0.007 : pose == 1 ? 0.021 : PI_D / 4;
+            K.target = (float)rand_uniform(c.seed, genv, rc, 6, lo, hi);
+        }
+        K.flags = (K.flags & ~(7 << FL_POSE_SHIFT)) | (pose << FL_POSE_SHIFT);
     }
     if (leg == 0) {
         P.si[I_RESETCNT * (size_t)N + env] = (int32_t)rc;
@@ -1231,7 +1278,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     const RexSimConfig& c = P.cfg;
     constexpr int A = (TASK == REXSIM_TASK_WALK) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 8)
                     : (TASK == REXSIM_TASK_GALLOP) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 4)
-                    : (TASK == REXSIM_TASK_TURN) ? 2 : 1;
+                    : (TASK == REXSIM_TASK_TURN) ? 2 : 1;     // standup, poses: 1
     const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
 
     Lane L; Task K; Arm AR;
@@ -1275,6 +1322,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     float reward;
     M3 R = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
     if (TASK == REXSIM_TASK_TURN) reward = 0.035f - fabsf(L.pos.x) - fabsf(L.pos.y);
+    else if (TASK == REXSIM_TASK_POSES) reward = 1.0f;                // poses_env.py:256-258
     else if (TASK == REXSIM_TASK_STANDUP) {
         float pr = fabsf(L.pos.x) + fabsf(L.pos.y) + fabsf(0.21f - L.pos.z);
         pr = (fabsf(pr) < 0.1f) ? 1.0f - pr : -pr;
@@ -1302,6 +1350,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     // ---- termination ----------------------------------------------------------------------------------------
     bool done;
     if (TASK == REXSIM_TASK_WALK || TASK == REXSIM_TASK_TURN) done = (R.c2.z < 0.85f) || (K.flags & FL_ENVGOAL);
+    else if (TASK == REXSIM_TASK_POSES) done = false;                 // is_fallen() returns False (poses_env.py:247-254)
     else {
         float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
         bool fallen = fabsf(rpy[0]) > 0.3f || fabsf(rpy[1]) > 0.5f;
@@ -1382,8 +1431,10 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     float ip[3];
     if (task == REXSIM_TASK_STANDUP) { ip[0] = (leg & 1) ? 0.4f : -0.4f; ip[1] = -1.5f; ip[2] = 6.f; }
     else init_pose(signal, leg, ip);
-    for (int it = 0; it < 100; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
-    const int n2 = (int)(0.5 / P.cfg.sim_dt_d);
+    // RexPosesEnv.reset -> RexGymEnv.reset(initial_motor_angles=None): Rex.Reset skips both holding phases (rex.py:307)
+    const int n1 = (task == REXSIM_TASK_POSES) ? 0 : 100;
+    for (int it = 0; it < n1; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
+    const int n2 = (task == REXSIM_TASK_POSES) ? 0 : (int)(0.5 / P.cfg.sim_dt_d);
     for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
     {
         float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
@@ -1399,6 +1450,69 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// host-side launchers (called from rexsim_capi.cu)
+//
+// Compile units: the file is compiled once per (task, signal) pair with -DREXSIM_UNIT=<k> (k = 0..7, only that
+// pair's step kernels are instantiated) and once with -DREXSIM_UNIT=100 (reset / settle / get / set kernels and the
+// dispatcher); rex_gym_b200/build.py runs the units in parallel.  Without REXSIM_UNIT everything is one unit.
+// -------------------------------------------------------------------------------------------------
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT < 100
+template <int TASK, int SIGNAL, bool ARM>
+static cudaError_t launch_step_tsa(const Params& P, cudaStream_t st) {
+    int threads = REXSIM_BLOCK;
+    int blocks = (P.N * 4 + threads - 1) / threads;
+    // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover, DESIGN.md)
+    const bool big = !ARM && blocks > 4 * P.sm_count;
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM><<<blocks, threads, 0, st>>>(P);
+    } else {
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM><<<blocks, threads, 0, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+template <int TASK, int SIGNAL>
+static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
+    // the arm (mark='arm') is built for the standup task (BASELINE config 5) and the walk-ik task
+    constexpr bool HAS_ARM = (TASK == REXSIM_TASK_STANDUP || (TASK == REXSIM_TASK_WALK && SIGNAL == REXSIM_SIGNAL_IK));
+    if (P.cfg.num_motors == 18) {
+        if (HAS_ARM) return launch_step_tsa<TASK, SIGNAL, HAS_ARM>(P, st);
+        return cudaErrorNotSupported;
+    }
+    return launch_step_tsa<TASK, SIGNAL, false>(P, st);
+}
+#endif
+#define REXSIM_STEP_UNIT(k, T, S) \
+    cudaError_t launch_step_unit_##k(const Params& P, cudaStream_t st) { return launch_step_ts<T, S>(P, st); }
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 0
+REXSIM_STEP_UNIT(0, REXSIM_TASK_WALK, REXSIM_SIGNAL_IK)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 1
+REXSIM_STEP_UNIT(1, REXSIM_TASK_WALK, REXSIM_SIGNAL_OL)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 2
+REXSIM_STEP_UNIT(2, REXSIM_TASK_GALLOP, REXSIM_SIGNAL_IK)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 3
+REXSIM_STEP_UNIT(3, REXSIM_TASK_GALLOP, REXSIM_SIGNAL_OL)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 4
+REXSIM_STEP_UNIT(4, REXSIM_TASK_TURN, REXSIM_SIGNAL_IK)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 5
+REXSIM_STEP_UNIT(5, REXSIM_TASK_TURN, REXSIM_SIGNAL_OL)
+#endif
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 6
+REXSIM_STEP_UNIT(6, REXSIM_TASK_STANDUP, REXSIM_SIGNAL_OL)
+#endif
+
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 7
+REXSIM_STEP_UNIT(7, REXSIM_TASK_POSES, REXSIM_SIGNAL_IK)
+#endif
+
+#if !defined(REXSIM_UNIT) || REXSIM_UNIT == 100
 // -------------------------------------------------------------------------------------------------
 // get / set physical state
 // -------------------------------------------------------------------------------------------------
@@ -1429,39 +1543,21 @@ __global__ void set_state_kernel(const Params P, const float* in_f) {
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-// host-side launchers (called from rexsim_capi.cu)
-// -------------------------------------------------------------------------------------------------
-template <int TASK, int SIGNAL, bool ARM>
-static cudaError_t launch_step_tsa(const Params& P, cudaStream_t st) {
-    int threads = REXSIM_BLOCK;
-    int blocks = (P.N * 4 + threads - 1) / threads;
-    // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover, DESIGN.md)
-    const bool big = !ARM && blocks > 4 * P.sm_count;
-    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM><<<blocks, threads, 0, st>>>(P);
-    } else {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM><<<blocks, threads, 0, st>>>(P);
-    }
-    return cudaGetLastError();
-}
-template <int TASK, int SIGNAL>
-static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
-    // the arm (mark='arm') is built for the standup task (BASELINE config 5) and the walk task
-    if (P.cfg.num_motors == 18) {
-        if (TASK == REXSIM_TASK_STANDUP || (TASK == REXSIM_TASK_WALK && SIGNAL == REXSIM_SIGNAL_IK)) return launch_step_tsa<TASK, SIGNAL, (TASK == REXSIM_TASK_STANDUP || (TASK == REXSIM_TASK_WALK && SIGNAL == REXSIM_SIGNAL_IK))>(P, st);
-        return cudaErrorNotSupported;
-    }
-    return launch_step_tsa<TASK, SIGNAL, false>(P, st);
-}
+cudaError_t launch_step_unit_0(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_1(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_2(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_3(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_4(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_5(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_6(const Params&, cudaStream_t);
+cudaError_t launch_step_unit_7(const Params&, cudaStream_t);
 cudaError_t launch_step(const Params& P, cudaStream_t st) {
     const int t = P.cfg.task, s = P.cfg.signal;
-    if (t == REXSIM_TASK_WALK) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_WALK, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_WALK, REXSIM_SIGNAL_OL>(P, st);
-    if (t == REXSIM_TASK_GALLOP) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_GALLOP, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_GALLOP, REXSIM_SIGNAL_OL>(P, st);
-    if (t == REXSIM_TASK_TURN) return s == REXSIM_SIGNAL_IK ? launch_step_ts<REXSIM_TASK_TURN, REXSIM_SIGNAL_IK>(P, st) : launch_step_ts<REXSIM_TASK_TURN, REXSIM_SIGNAL_OL>(P, st);
-    return launch_step_ts<REXSIM_TASK_STANDUP, REXSIM_SIGNAL_OL>(P, st);
+    if (t == REXSIM_TASK_WALK) return s == REXSIM_SIGNAL_IK ? launch_step_unit_0(P, st) : launch_step_unit_1(P, st);
+    if (t == REXSIM_TASK_GALLOP) return s == REXSIM_SIGNAL_IK ? launch_step_unit_2(P, st) : launch_step_unit_3(P, st);
+    if (t == REXSIM_TASK_TURN) return s == REXSIM_SIGNAL_IK ? launch_step_unit_4(P, st) : launch_step_unit_5(P, st);
+    if (t == REXSIM_TASK_POSES) return launch_step_unit_7(P, st);
+    return launch_step_unit_6(P, st);
 }
 cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st) {
     int k = P.reset_idx ? P.reset_k : P.N;
@@ -1492,5 +1588,7 @@ cudaError_t launch_set_state(const Params& P, const float* in_f, cudaStream_t st
     set_state_kernel<<<(P.N + 127) / 128, 128, 0, st>>>(P, in_f);
     return cudaGetLastError();
 }
+
+#endif  // unit 100
 
 }  // namespace rexsim

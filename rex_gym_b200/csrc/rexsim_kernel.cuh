@@ -37,7 +37,8 @@ enum {
 enum {
     FL_GOAL = 1, FL_TERMINATING = 2, FL_STILL = 4, FL_BACKWARDS = 8, FL_CLOCKWISE = 16, FL_ENVGOAL = 32,
     FL_ENABLED_SHIFT = 8,  // 12 leg motor-enabled bits
-    FL_ARM_ENABLED_SHIFT = 20   // 6 arm motor-enabled bits
+    FL_ARM_ENABLED_SHIFT = 20,  // 6 arm motor-enabled bits
+    FL_POSE_SHIFT = 26          // 3 bits: poses task, which base coordinate is staged (0 base_y, 1 base_z, 2 roll, 3 pitch, 4 yaw)
 };
 
 struct Params {

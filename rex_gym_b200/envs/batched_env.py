@@ -18,13 +18,14 @@ from ..model_tables import pack_model_tables, TOE_MARGIN
 from ..terrain import make_random_fields
 from .spaces import Box
 
-TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3}
+TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3, "poses": 4}
 SIGNALS = {"ik": 0, "ol": 1}
 TERRAINS = {"plane": 0, "random": 1}
 DEFAULT_URDF_VERSION = "default"
 OBSERVATION_EPS = 0.01          # rex_gym/envs/rex_gym_env.py:19
 ACTION_BOUND = {("walk", "ik"): 0.4, ("walk", "ol"): 0.01, ("gallop", "ik"): 0.4, ("gallop", "ol"): 0.3,
-                ("turn", "ik"): 0.01, ("turn", "ol"): 0.01, ("standup", "ol"): 0.1, ("standup", "ik"): 0.1}
+                ("turn", "ik"): 0.01, ("turn", "ol"): 0.01, ("standup", "ol"): 0.1, ("standup", "ik"): 0.1,
+                ("poses", "ik"): 0.1, ("poses", "ol"): 0.1}
 
 ERR_NONFINITE, ERR_JOINT_LIMIT, ERR_BODY_CONTACT = 1, 2, 4
 
@@ -76,7 +77,8 @@ class BatchedRexEnv(object):
                  log_path=None, target_position=None, backwards=None, target_orient=None, init_orient=None,
                  energy_weight=None, signal_type="ik", terrain_type="plane", terrain_id=None, mark="base",
                  normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
-                 motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0):
+                 motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0,
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None):
         if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
             raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
         if task not in TASKS or signal_type not in SIGNALS:
@@ -97,8 +99,8 @@ class BatchedRexEnv(object):
         self.device = torch.device(device)
         self.num_envs = int(num_envs)
         self.num_motors = 12 if mark == "base" else 18
-        rep = action_repeat or (6 if task == "gallop" else 5)
-        cts = control_time_step or (0.006 if task == "gallop" else 0.005)
+        rep = action_repeat or (6 if task in ("gallop", "poses") else 5)
+        cts = control_time_step or (0.006 if task in ("gallop", "poses") else 0.005)
         self.control_time_step, self._action_repeat = cts, rep
         self._time_step = cts / rep
         if mark not in ("base", "arm"):
@@ -119,6 +121,8 @@ class BatchedRexEnv(object):
         c.w_distance, c.w_drift, c.w_shake = 1.0, 2.0, 0.005                            # rex_gym_env.py:56-59
         c.w_energy = energy_weight if energy_weight is not None else (0.005 if task == "gallop" else 0.0005)
         c.normalize, c.max_episode_steps, c.auto_reset, c.seed = int(normalize), int(max_episode_steps), int(auto_reset), seed
+        for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):      # poses_env.py:49-53 (None = rotate per reset)
+            c.pose_values[k] = float("nan") if v is None else float(v)
         self._fields = None
         with torch.cuda.device(self.device):
             if terrain_type == "random":
@@ -140,20 +144,23 @@ class BatchedRexEnv(object):
         self.action_dim = self._L.rexsim_action_dim(c.task, c.signal)
         N, O, A = self.num_envs, self.obs_dim, self.action_dim
         dev = self.device
-        # obs | reward | done live in ONE device allocation mirrored by ONE pinned host block, so the host path of
-        # step() is one H2D copy (actions) and one D2H copy (all results) per step
+        # device path: obs | reward | done of the last step (torch views; `done` is a bool view of the u8 the kernel writes)
+        self._obs = torch.zeros((N, O), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros((N,), dtype=torch.float32, device=dev)
+        self._done_u8 = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        self._done = self._done_u8.view(torch.bool)
+        # host path (numpy in / numpy out): ONE pinned block each way, filled by rexsim_step_host in one C call
         nb_obs, nb_rew = N * O * 4, N * 4
-        self._out = torch.zeros((nb_obs + nb_rew + ((N + 3) // 4) * 4,), dtype=torch.uint8, device=dev)
-        self._obs = self._out[:nb_obs].view(torch.float32).view(N, O)
-        self._reward = self._out[nb_obs:nb_obs + nb_rew].view(torch.float32)
-        self._done = self._out[nb_obs + nb_rew:nb_obs + nb_rew + N]
-        self._act = torch.zeros((N, A), dtype=torch.float32, device=dev)
+        nb_out = int(self._L.rexsim_host_out_bytes(self._h))
         self._h_act = torch.zeros((N, A), dtype=torch.float32).pin_memory()
-        self._h_out = torch.zeros_like(self._out, device="cpu").pin_memory()
-        self._h_obs = self._h_out[:nb_obs].view(torch.float32).view(N, O)
-        self._h_reward = self._h_out[nb_obs:nb_obs + nb_rew].view(torch.float32)
-        self._h_done = self._h_out[nb_obs + nb_rew:nb_obs + nb_rew + N]
-        self._h_err = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._h_out = torch.zeros((nb_out,), dtype=torch.uint8).pin_memory()
+        self._h_act_np = self._h_act.numpy()
+        ho = self._h_out.numpy()
+        self._h_obs = ho[:nb_obs].view(np.float32).reshape(N, O)
+        self._h_reward = ho[nb_obs:nb_obs + nb_rew].view(np.float32)
+        self._h_done = ho[nb_obs + nb_rew:nb_obs + nb_rew + N].view(np.bool_)
+        self._h_err = ho[nb_out - 4:].view(np.int32)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         p = C.c_void_p()
         _capi.check(self._L.rexsim_error_flags(self._h, C.byref(p)))
         self._err = torch.as_tensor(_DevArray(p.value, (N + 1,), "<i4", self), device=dev)
@@ -191,34 +198,35 @@ class BatchedRexEnv(object):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def step(self, action):
-        """BatchEnv.step (batch_env.py:63-90).  numpy in -> numpy out (host buffers, copies inside);
-        CUDA tensor in -> CUDA tensors out (no host traffic)."""
+        """BatchEnv.step (batch_env.py:63-90).  numpy in -> numpy out (host buffers: one rexsim_step_host call = H2D copy,
+        kernel, D2H copy, wait);  CUDA tensor in -> CUDA tensors out (one asynchronous kernel launch, no host traffic)."""
         N, A = self.num_envs, self.action_dim
-        on_device = isinstance(action, torch.Tensor) and action.is_cuda
-        with torch.cuda.device(self.device):
-            if on_device:
-                if tuple(action.shape) != (N, A):
-                    raise ValueError("Invalid action shape %s, expected %s" % (tuple(action.shape), (N, A)))
-                act = action.to(torch.float32).contiguous()
+        if isinstance(action, torch.Tensor) and action.is_cuda:
+            if tuple(action.shape) != (N, A):
+                raise ValueError("Invalid action shape %s, expected %s" % (tuple(action.shape), (N, A)))
+            if action.dtype != torch.float32 or not action.is_contiguous():
+                action = action.to(torch.float32).contiguous()
+            if torch.cuda.current_device() != self._dev_index:
+                with torch.cuda.device(self.device):
+                    rc = self._L.rexsim_step(self._h, action.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(),
+                                             self._done_u8.data_ptr(), self._stream())
             else:
-                a = np.asarray(action, dtype=np.float32)
-                if a.shape != (N, A):
-                    raise ValueError("Invalid action shape %s, expected %s" % (a.shape, (N, A)))
-                if not np.isfinite(a).all():
-                    raise ValueError("Invalid action: non-finite values")
-                self._h_act.numpy()[...] = a
-                self._act.copy_(self._h_act, non_blocking=True)
-                act = self._act
-            _capi.check(self._L.rexsim_step(self._h, act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(),
-                                            self._done.data_ptr(), self._stream()))
-            if on_device:
-                return self._obs, self._reward, self._done.bool(), _Info(self)
-            self._h_out.copy_(self._out, non_blocking=True)
-            self._h_err.copy_(self._err[N:N + 1], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+                rc = self._L.rexsim_step(self._h, action.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(),
+                                         self._done_u8.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            if rc:
+                _capi.check(rc)
+            return self._obs, self._reward, self._done, _Info(self)
+        a = np.asarray(action, dtype=np.float32)
+        if a.shape != (N, A):
+            raise ValueError("Invalid action shape %s, expected %s" % (a.shape, (N, A)))
+        if not np.isfinite(a).all():
+            raise ValueError("Invalid action: non-finite values")
+        np.copyto(self._h_act_np, a)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.rexsim_step_host(self._h, self._h_act.data_ptr(), self._h_out.data_ptr(), self._stream()))
         if int(self._h_err[0]) & ERR_NONFINITE:
             raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
-        return self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), self._h_done.numpy().astype(bool), _Info(self)
+        return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), _Info(self)
 
     def reset(self, indices=None):
         """BatchEnv.reset (batch_env.py:92-109): observations of the reset environments."""
@@ -332,6 +340,14 @@ class RexTurnBatchEnv(BatchedRexEnv):
         super().__init__(task="turn", num_envs=num_envs, **kw)
 
 
+class RexPosesBatchEnv(BatchedRexEnv):
+    """rex_gym/envs/gym/poses_env.py:21 RexPosesEnv, batched (no settle at reset; reward 1, never 'fallen')."""
+
+    def __init__(self, num_envs=1, **kw):
+        kw.setdefault("control_time_step", 0.006); kw.setdefault("action_repeat", 6)
+        super().__init__(task="poses", num_envs=num_envs, **kw)
+
+
 class RexStandupBatchEnv(BatchedRexEnv):
     """rex_gym/envs/gym/standup_env.py:17 RexStandupEnv, batched (starts from INIT_POSES['rest_position'])."""
 
@@ -343,11 +359,18 @@ class RexStandupBatchEnv(BatchedRexEnv):
 
 # gym ids of rex_gym/playground/__init__.py:17-57 -> batched classes
 ENV_IDS = {"RexWalk-v0": RexWalkBatchEnv, "RexGalloping-v0": RexGallopBatchEnv, "RexTurn-v0": RexTurnBatchEnv,
-           "RexStandup-v0": RexStandupBatchEnv}
+           "RexStandup-v0": RexStandupBatchEnv, "RexPoses-v0": RexPosesBatchEnv}
+
+
+# max_episode_steps of the reference's registrations (playground/__init__.py:17-57): gym.make wraps the env in a TimeLimit
+REGISTERED_MAX_EPISODE_STEPS = {"RexWalk-v0": 2500, "RexGalloping-v0": 1000, "RexTurn-v0": 1000, "RexStandup-v0": 400,
+                                "RexPoses-v0": 400}
 
 
 def make(env_id, num_envs=1, **kwargs):
-    """gym.make(id, **args) equivalent (rex_gym/playground/trainer.py:47) returning a whole batch."""
+    """gym.make(id, **args) equivalent (rex_gym/playground/trainer.py:47) returning a whole batch; the registered
+    max_episode_steps (gym's TimeLimit) is fused into the kernel unless the caller overrides it."""
     if env_id not in ENV_IDS:
         raise ValueError("env id %r not built (have %s)" % (env_id, sorted(ENV_IDS)))
+    kwargs.setdefault("max_episode_steps", REGISTERED_MAX_EPISODE_STEPS[env_id])
     return ENV_IDS[env_id](num_envs=num_envs, **kwargs)

@@ -98,10 +98,16 @@ class RexStandupEnv(SingleRexEnv):
         super().__init__(**kwargs)
 
 
+class RexPosesEnv(SingleRexEnv):
+    """rex_gym/envs/gym/poses_env.py:21"""
+    _task = "poses"
+
+
 def register_with_gym():
     """The reference registers its ids at import of rex_gym.playground (playground/__init__.py:17-57); call this to
     register the same ids against the B200 envs when gym is installed."""
     from gym.envs.registration import register  # type: ignore
-    for env_id, entry, steps in (("RexWalk-v0", "RexWalkEnv", 2000), ("RexGalloping-v0", "RexReactiveEnv", 2000),
-                                 ("RexTurn-v0", "RexTurnEnv", 1000), ("RexStandup-v0", "RexStandupEnv", 500)):
+    for env_id, entry, steps in (("RexWalk-v0", "RexWalkEnv", 2500), ("RexGalloping-v0", "RexReactiveEnv", 1000),
+                                 ("RexTurn-v0", "RexTurnEnv", 1000), ("RexStandup-v0", "RexStandupEnv", 400),
+                                 ("RexPoses-v0", "RexPosesEnv", 400)):
         register(id=env_id, entry_point="rex_gym_b200.envs.single_env:" + entry, max_episode_steps=steps, reward_threshold=5.0)

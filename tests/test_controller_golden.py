@@ -102,3 +102,47 @@ def test_env_signal_reward_termination_obs(idx):
         assert d == st["done"], f"done step {k}"
         np.testing.assert_allclose(obs, st["obs"], rtol=0, atol=1e-12, err_msg=f"obs step {k}")
         assert [e.goal_reached, e.stay_still, e.env_goal_reached] == st["flags"], f"flags step {k}"
+
+
+# ---- RexPosesEnv (envs/gym/poses_env.py), fixture tests/golden/poses_golden.json.gz ------------------------
+POSES = json.loads(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "poses_golden.json.gz")).read())
+
+
+def test_poses_reset_rotation():
+    """deque rotation base_y, base_z, roll, pitch, yaw (rex_gym_env.py:259; poses_env.py:159-162): the constructor's own
+    reset() consumes the first entry, so the k-th user-visible reset (reset_count k) lands on entry k mod 5."""
+    names = ["base_y", "base_z", "roll", "pitch", "yaw"]
+    sim = O.OracleSim(1, "poses", "ik", settle=False)
+    lo_hi = {0: (-0.007, 0.007), 1: (-0.048, 0.021), 2: (-math.pi / 4, math.pi / 4), 3: (-math.pi / 4, math.pi / 4), 4: (-math.pi / 4, math.pi / 4)}
+    for r in POSES["rotation"][1:]:
+        sim.reset()
+        e = sim.env(0)
+        assert e.reset_count == r["reset_index"]
+        assert names[e.next_pose] == r["next_pose"] and r["in_range"]
+        lo, hi = lo_hi[e.next_pose]
+        assert lo <= e.target_value <= hi
+
+
+@pytest.mark.parametrize("idx", range(len(POSES["envs"])))
+def test_poses_signal_reward_obs(idx):
+    g = POSES["envs"][idx]
+    a = g["args"]
+    sim = O.OracleSim(1, "poses", "ik", settle=False, base_y=a["base_y"], base_z=a["base_z"], base_roll=a["base_roll"],
+                      base_pitch=a["base_pitch"], base_yaw=a["base_yaw"])
+    sim.reset()
+    e = sim.env(0)
+    assert e.next_pose == g["next_pose"] and e.target_value == g["target_value"]
+    for k, st in enumerate(g["steps"]):
+        assert abs(e.step_counter * g["dt"] - st["t"]) < 1e-15
+        cmd = sim.transform_action(st["action"])
+        np.testing.assert_allclose(cmd, st["cmd"], rtol=0, atol=TOL, err_msg=f"step {k}")
+        e.step_counter += g["repeat"]
+        pos, rpy, angvel, q, qd, tau = scripted_state(k, 0.0, 0.0, 0.0, g["repeat"], g["dt"], None)
+        quat = euler_to_quat(rpy)
+        for c in range(3):
+            e.pos[c], e.angvel[c] = pos[c], angvel[c]
+        for c in range(4):
+            e.quat[c] = quat[c]
+        r, d, obs = sim.reward_done_obs()
+        assert r == st["reward"] == 1.0 and d == st["done"] is False
+        np.testing.assert_allclose(obs, st["obs"], rtol=0, atol=1e-12, err_msg=f"obs step {k}")

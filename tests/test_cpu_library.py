@@ -90,7 +90,7 @@ def test_no_cpu_fallback():
 
 def test_reference_surface_names():
     import rex_gym_b200 as R
-    assert set(R.ENV_IDS) == {"RexWalk-v0", "RexGalloping-v0", "RexTurn-v0", "RexStandup-v0"}       # playground/__init__.py:17-57
+    assert set(R.ENV_IDS) == {"RexWalk-v0", "RexGalloping-v0", "RexTurn-v0", "RexStandup-v0", "RexPoses-v0"}       # playground/__init__.py:17-57
     for m in ("step", "reset", "close", "__len__", "__getitem__"):                  # batch_env.py:44-115
         assert hasattr(R.BatchedRexEnv, m)
     with pytest.raises(ValueError):

@@ -77,7 +77,9 @@ CASES = [("walk", "ik", dict(target_position=2.0, backwards=False)),
          ("turn", "ol", dict()),
          ("standup", "ol", dict()),
          ("standup", "ol", dict(mark="arm")),                      # BASELINE config 5 model: 18 DOF, arm limit rows always active
-         ("walk", "ik", dict(mark="arm", target_position=2.0, backwards=True))]
+         ("walk", "ik", dict(mark="arm", target_position=2.0, backwards=True)),
+         ("poses", "ik", dict()),                                   # RexPosesEnv: pose rotates per reset, target drawn in range
+         ("poses", "ik", dict(base_y=0.0, base_z=0.0, base_roll=0.0, base_pitch=0.4, base_yaw=0.0))]
 
 
 def test_loaded_library_is_the_in_tree_cuda_build():
@@ -102,8 +104,10 @@ def test_reset_settle_and_draws(task, sig, kw):
     assert np.abs(sg["quat"] - so["quat"]).max() < tq
     np.testing.assert_allclose(og, oc, atol=10 * tq)
     sf, si = env._state_f.cpu().numpy(), env._state_i.cpu().numpy()
-    tp = np.array([ora.env(i).target_position for i in range(n)], np.float32)
+    tp = np.array([ora.env(i).target_value if task == "poses" else ora.env(i).target_position for i in range(n)], np.float32)
     np.testing.assert_array_equal(sf[38], tp)                                         # F_TARGET
+    if task == "poses":
+        np.testing.assert_array_equal((si[2] >> 26) & 7, [ora.env(i).next_pose for i in range(n)])   # FL_POSE_SHIFT
     np.testing.assert_array_equal(sf[41], np.array([ora.env(i).kp for i in range(n)], np.float32))
     np.testing.assert_array_equal(sf[42], np.array([ora.env(i).kd for i in range(n)], np.float32))
     np.testing.assert_array_equal(si[3], [ora.env(i).reset_count for i in range(n)])  # I_RESETCNT

@@ -307,5 +307,84 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def poses_golden(pb):
+    """RexPosesEnv (envs/gym/poses_env.py): reset's pose rotation + _signal / _reward / _termination / _get_observation,
+    written to tests/golden/poses_golden.json.gz (a separate fixture so the first one keeps its bytes)."""
+    import collections
+    import gzip
+    from rex_gym.model import rex_constants
+    from rex_gym.envs.gym import poses_env
+    rng = np.random.default_rng(20260923)
+    out = {"reference": "nicrusso7/rex-gym @ /root/reference", "shims": ["stub gym/pybullet/pybullet_data", "scripted fake rex"],
+           "envs": [], "rotation": []}
+
+    def make_env(**pose_args):
+        env = object.__new__(poses_env.RexPosesEnv)
+        env._pybullet_client = pb
+        env.mark = "base"
+        env._is_render = False
+        env.manual_control = False
+        env.load_ui = True
+        env._time_step = 0.001
+        for k in ("base_y", "base_z", "base_roll", "base_pitch", "base_yaw"):
+            setattr(env, "_" + k, pose_args.get(k))
+        env._queue = collections.deque(["base_y", "base_z", "roll", "pitch", "yaw"])         # rex_gym_env.py:259-267
+        env._ranges = {"base_x": (-0.02, 0.02, 0.01), "base_y": (-0.007, 0.007, 0), "base_z": (-0.048, 0.021, 0),
+                       "roll": (-np.pi / 4, np.pi / 4, 0), "pitch": (-np.pi / 4, np.pi / 4, 0), "yaw": (-np.pi / 4, np.pi / 4, 0)}
+        env.env_goal_reached = False
+        env.rex = FakeRex(0.001)
+        env.rex.initial_pose = rex_constants.INIT_POSES["stand"]
+        return env
+
+    def reset_tail(env):
+        """The body of RexPosesEnv.reset after super().reset() (poses_env.py:148-165), run verbatim on the object."""
+        if env._base_y is not None or env._base_z is not None or env._base_roll is not None \
+                or env._base_pitch is not None or env._base_yaw is not None:
+            env.fill_next_pose_and_target()
+        else:
+            env.next_pose = env._queue.popleft()
+            env._queue.append(env.next_pose)
+            env.target_value = random.uniform(env._ranges[env.next_pose][0], env._ranges[env.next_pose][1])
+        env.values = env._ranges.copy()
+
+    # deque rotation over successive resets: construction calls reset() once, the user's resets follow
+    env = make_env()
+    for k in range(12):
+        reset_tail(env)
+        out["rotation"].append(dict(reset_index=k, next_pose=env.next_pose,
+                                    in_range=bool(env._ranges[env.next_pose][0] <= env.target_value <= env._ranges[env.next_pose][1])))
+    cases = [dict(base_y=0.005, base_z=0.0, base_roll=0.0, base_pitch=0.0, base_yaw=0.0),
+             dict(base_y=0.0, base_z=-0.03, base_roll=0.0, base_pitch=0.0, base_yaw=0.0),
+             dict(base_y=0.0, base_z=0.0, base_roll=0.5, base_pitch=0.0, base_yaw=0.0),
+             dict(base_y=0.0, base_z=0.0, base_roll=0.0, base_pitch=-0.6, base_yaw=0.0),
+             dict(base_y=0.0, base_z=0.0, base_roll=0.0, base_pitch=0.0, base_yaw=0.7),
+             dict(base_y=0.0, base_z=0.0, base_roll=0.0, base_pitch=0.0, base_yaw=0.0)]
+    names = ["base_y", "base_z", "roll", "pitch", "yaw"]
+    for pa in cases:
+        env = make_env(**pa)
+        reset_tail(env)
+        steps = []
+        rex = env.rex
+        for k in range(200):
+            action = rng.uniform(-0.1, 0.1, 1)
+            t_pre = rex.GetTimeSinceReset()
+            cmd = np.asarray(poses_env.RexPosesEnv._convert_from_leg_model(env._signal(t_pre, action.copy()))).astype(float)
+            rex.step_counter += 6
+            pos, rpy, angvel, q, qd, tau = scripted_state(k, 0.0, 0.0, 0.0, 6, rex.dt, None)
+            rex.pos, rex.quat, rex.angvel = pos, euler_to_quat(rpy), angvel
+            steps.append(dict(t=t_pre, action=action.tolist(), cmd=cmd.tolist(), reward=float(env._reward()),
+                              done=bool(env.is_fallen()), obs=np.asarray(env._get_observation()).astype(float).tolist()))
+        out["envs"].append(dict(args=pa, next_pose=names.index(env.next_pose), target_value=float(env.target_value),
+                                repeat=6, dt=0.001, steps=steps))
+    path = os.path.join(os.path.dirname(OUT), "poses_golden.json.gz")
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out).encode())
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--poses-only" in sys.argv:
+        poses_golden(install_stubs())
+    else:
+        main()
+        poses_golden(sys.modules["pybullet"])
