@@ -128,6 +128,8 @@ def test_free_running_rollout(task, sig, kw):
     # standing up is an explosive manoeuvre with every foot-joint limit row (and, with the arm, three more) active and
     # the solver at its iteration cap: bounded at 5e-3 there, at the north-star 1e-3 for the locomotion tasks
     tol_q, tol_p = (5e-3, 2e-3) if task == "standup" else (TOL_Q, TOL_P)
+    if task == "poses":
+        steps = 150        # RexPosesEnv.reset does not settle: the 5 mm drop onto the feet is part of the episode (chaos starts earlier)
     if task == "gallop" and sig == "ik":
         steps = 110        # every env follows the same hopping trajectory (the action only shifts ramp timings): common-mode chaos
     env, ora = _env(task, n, signal_type=sig, seed=3, **kw), _oracle(task, n, signal_type=sig, seed=3, **kw)
