@@ -55,11 +55,12 @@ enum {
     REXSIM_FLAG_TILE_MISS = 8,        /* a contact query fell outside the 0.8 m heightfield window staged in shared memory */
 };
 
-#define REXSIM_MAX_TOE_PTS 32
+#define REXSIM_MAX_TOE_PTS 96
 /* float offsets inside the model table (see rex_gym_b200/model_tables.py for the packer) */
-#define REXSIM_MT_BASE 0            /* mass, com[3], inertia[6](xx,yy,zz,xy,xz,yz), root_mass, root_inertia[3], diag flag, pad */
+#define REXSIM_MT_BASE 0            /* mass, com[3], inertia[6](xx,yy,zz,xy,xz,yz), root_mass, root_inertia[3], diag flag, toe half width */
 #define REXSIM_MT_LEG 16            /* [4 legs][3 bodies][16]: jpos[3], mass, com[3], lower, inertia[6], upper, diag flag */
-#define REXSIM_MT_TOE (16 + 192)    /* [4 legs][REXSIM_MAX_TOE_PTS][3] toe hull sample points, foot-body frame */
+#define REXSIM_MT_TOE (16 + 192)    /* 384 floats: [toe_npts <= REXSIM_MAX_TOE_PTS][2] (x, z) profile of the toe prism in the foot-body frame
+                                     * (the hull of stl/foot.stl is this profile extruded over y in [-w, w]; identical on the 4 feet) */
 #define REXSIM_MT_BOX (16 + 192 + 384)         /* [4 legs][3 bodies][8 corners][3] collision box corners, body frame */
 #define REXSIM_MT_BASEBOX (16 + 192 + 384 + 288) /* [3 boxes][8][3] base + chassis boxes */
 #define REXSIM_MT_FLOATS (16 + 192 + 384 + 288 + 72)
@@ -90,7 +91,7 @@ typedef struct {
     float friction;                   /* combined link x ground lateral friction */
     float residual_threshold;         /* solver early-out (pybullet default 1e-7) */
     float erp_contact, erp_joint;
-    int32_t toe_npts;                 /* valid points per toe in the model table */
+    int32_t toe_npts;                 /* profile vertices of the toe prism in the model table */
     float toe_margin;
     int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */
     float pose_values[5];             /* poses task: base_y, base_z, base_roll, base_pitch, base_yaw constructor arguments

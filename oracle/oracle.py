@@ -12,9 +12,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-MODEL_DIR = os.path.join(HERE, "..", "rex_gym_b200", "model")
+MODEL_DIR = os.environ.get("REXO_MODEL_DIR") or os.path.join(HERE, "..", "rex_gym_b200", "model")
 
-MAXB, MAXDOF, MAXSHAPE, MAXPTS = 20, 18, 40, 400
+MAXB, MAXDOF, MAXSHAPE, MAXPTS = 20, 18, 40, 1024
 TASKS = {"walk": 0, "gallop": 1, "turn": 2, "standup": 3, "poses": 4}
 SIGNALS = {"ik": 0, "ol": 1}
 TERRAINS = {"plane": 0, "random": 1}
@@ -29,6 +29,7 @@ class RexoModel(C.Structure):
         ("root_mass", C.c_double), ("root_inertia", C.c_double * 3),
         ("nshape", C.c_int32), ("shape_start", C.c_int32 * MAXSHAPE), ("shape_npts", C.c_int32 * MAXSHAPE),
         ("shape_enabled", C.c_int32 * MAXSHAPE), ("pt_body", C.c_int32 * MAXPTS), ("pt_margin", C.c_double * MAXPTS),
+        ("pt_terrain", C.c_int32 * MAXPTS),
         ("pts", (C.c_double * 3) * MAXPTS),
         ("nmotor", C.c_int32), ("motor_dof", C.c_int32 * MAXDOF),
     ]
@@ -113,10 +114,14 @@ def _rpy_to_mat(rpy):
     return rz @ ry @ rx
 
 
-TOE_MARGIN = 0.001  # URDF importer default collision margin on convex hulls
+# Collision margin added to the toe hull's reach.  Bullet's URDF importer sets a 1 mm margin on convex hulls, but the PyBullet
+# trajectories recovered from the reference's checkpoints (tests/golden/pybullet_memory_golden.npz) put the touchdown of a
+# robot dropped from z = 0.21 where the EXACT hull without margin reaches the ground (1 mm of margin lands one control step
+# early in all 12 episodes; tools/dev_pybullet_replay.py), so the restatement uses 0.
+TOE_MARGIN = float(os.environ.get("REXO_TOE_MARGIN", 0.0))
 
 
-def load_model(mark="base", toes_only=False):
+def load_model(mark="base", toes_only=False, terrain_full_toe=False):
     """Model tables (tools/compile_urdf.py output) -> RexoModel."""
     with open(os.path.join(MODEL_DIR, f"rex_{mark}.json")) as f:
         j = json.load(f)
@@ -147,11 +152,14 @@ def load_model(mark="base", toes_only=False):
                 is_toe = sh["kind"] == "hull"
                 if toes_only and not is_toe:
                     continue
-                for p in sh["points"]:
+                nprof = len(sh["points"]) // 2 if is_toe else 0      # prism toe: profile on the y_lo side, then the y_hi side
+                for k, p in enumerate(sh["points"]):
                     for a in range(3):
                         m.pts[npts][a] = p[a]
                     m.pt_body[npts] = bi
                     m.pt_margin[npts] = TOE_MARGIN if is_toe else 0.0
+                    # heightfield terrain samples every 4th profile vertex (+ the last one) on both sides of the prism
+                    m.pt_terrain[npts] = 1 if (not is_toe or terrain_full_toe or (k % nprof) % 4 == 0 or (k % nprof) == nprof - 1) else 0
                     npts += 1
         m.shape_npts[gi] = npts - m.shape_start[gi]
     m.nshape = len(groups)
@@ -190,9 +198,9 @@ class OracleSim:
                  target_orient=None, init_orient=None, energy_weight=None, normalize=False,
                  max_episode_steps=0, seed=1234, nfields=0, fields=None, toes_only=False, settle=True,
                  solver_iterations=None, residual_threshold=1e-7, env_offset=0,
-                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None):
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, terrain_full_toe=False):
         self.L = lib(f32)
-        self.model, self.model_json = load_model(mark, toes_only=toes_only)
+        self.model, self.model_json = load_model(mark, toes_only=toes_only, terrain_full_toe=terrain_full_toe)
         c = RexoConfig()
         c.num_envs = num_envs
         c.task, c.signal, c.terrain = TASKS[task], SIGNALS[signal], TERRAINS[terrain]

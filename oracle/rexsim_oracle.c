@@ -557,7 +557,8 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
     }
     e->limit_rows = nlim;
     e->contact_mask = 0;
-    const real breaking = 0.0005, slop = 1e-5;
+    static double g_breaking = -1; if (g_breaking < 0) { const char* ev = getenv("REXO_BREAKING"); g_breaking = ev ? atof(ev) : 0.0005; }
+    const real breaking = g_breaking, slop = 1e-5;
     for (int sh = 0; sh < m->nshape; sh++) {    /* deepest sample point of each contact group vs ground */
         e->contact_vertex[sh] = -1;
         if (!m->shape_enabled[sh]) continue;
@@ -566,6 +567,7 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
         for (int v = 0; v < m->shape_npts[sh]; v++) {
             const int pi = m->shape_start[sh] + v;
             const int pb = m->pt_body[pi];
+            if (c->terrain == REXO_TERRAIN_RANDOM && !m->pt_terrain[pi]) continue;
             const double* pl = m->pts[pi];
             real lp[3] = {pl[0], pl[1], pl[2]}, wp[3], n[3], d;
             m3v(k->Rw[pb], lp, wp);
@@ -941,8 +943,11 @@ static void settle_state(RexoSim* s, RexoEnv* e) {   /* Rex.Reset: rex.py:296-32
         e->overheat[i] = 0; e->enabled[i] = 1; e->tau_obs[i] = 0; e->cmd[i] = 0;
     }
     e->step_counter = 0;
+    /* settle_on_reset == 2: pristine start -- joints placed at the task's init pose, no holding phase.  This is the state the
+     * PyBullet trajectories recovered from the reference's checkpoints start from (tools/extract_memory_golden.py). */
+    if (s->c.settle_on_reset == 2) for (int i = 0; i < m->nmotor; i++) e->q[m->motor_dof[i]] = s->init_pose[i];
     /* RexPosesEnv.reset calls RexGymEnv.reset() with initial_motor_angles=None: no holding phase (rex.py:307) */
-    if (s->c.settle_on_reset && s->c.task != REXO_TASK_POSES) {
+    if (s->c.settle_on_reset == 1 && s->c.task != REXO_TASK_POSES) {
         for (int it = 0; it < 100; it++) apply_action_and_step(s, e, s->stand_pose);     /* :315-318 */
         int n2 = (int)(0.5 / s->c.sim_dt);                                               /* reset_duration=0.5 */
         for (int it = 0; it < n2; it++) apply_action_and_step(s, e, s->init_pose);       /* :319-323 */

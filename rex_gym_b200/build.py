@@ -15,8 +15,9 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librexsim.so")
 STAMP = os.path.join(HERE, "librexsim.srchash")
 KERNEL_UNITS = [0, 1, 2, 3, 4, 5, 6, 7, 100]           # see the tail of rexsim_kernel.cu
-OTHER_SOURCES = ["rexsim_capi.cu"]
-HEADERS = ["rexsim_kernel.cuh", "rexsim_arm.cuh", os.path.join("..", "..", "include", "rexsim.h")]
+OTHER_SOURCES = ["rexsim_capi.cu", "rexsim_agent.cu"]
+HEADERS = ["rexsim_kernel.cuh", "rexsim_arm.cuh", os.path.join("..", "..", "include", "rexsim.h"),
+           os.path.join("..", "..", "include", "rexsim_agent.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"]
 NVCC_FLAGS = ARCH_FLAGS + ["-Xcompiler", "-fPIC"]
 

@@ -1,0 +1,480 @@
+// rexsim_agent.cu -- device-side agent glue around the step kernel (include/rexsim_agent.h):
+//   perform     : StreamingNormalize.transform + ForwardGaussianPolicy (policy MLP, value MLP) + sampling, one fused kernel
+//   experience  : StreamingNormalize.update for observations and rewards, one deterministic reduction kernel
+//   scans       : discounted_return / lambda_advantage (reference row semantics) and the done-aware time-major GAE
+// fp32 throughout (the reference's TF graph is fp32): the MLP is computed on the CUDA cores with a register-tiled
+// shared-memory GEMM so results match an fp32 reference to rounding; see DESIGN.md for the roofline of each kernel.
+#include "rexsim_kernel.cuh"
+#include "../../include/rexsim_agent.h"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace rexsim {
+void set_error(const char* msg);   // rexsim_capi.cu (message returned by rexsim_last_error)
+
+constexpr int AG_TM = 64;          // environments per tile
+constexpr int AG_MAX_O = 32, AG_MAX_A = 8, AG_MAX_H1 = 256, AG_MAX_H2 = 128;
+constexpr int RED_BLOCKS = 256;    // partial blocks of the filter update
+
+struct AgentDev {
+    RexAgentConfig cfg;
+    const float* __restrict__ params;    // policy block | value block
+    int pol_floats, val_floats;
+    float* filt;                          // observ mean[O], var_sum[O], reward mean, var_sum
+    int32_t* cnt;                         // observ count, reward count, step counter, blocks-done ticket
+    float* partial;                       // [RED_BLOCKS][2 * (O + 1)]
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// one 1-D TMA bulk copy global -> shared (weights of one network), completion on an mbarrier with explicit parity
+__device__ __forceinline__ void tma_bulk_load(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar, uint32_t parity) {
+    uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of the buffer vs the async write
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(gsrc), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+    }
+}
+
+struct PerformArgs {
+    AgentDev D;
+    const float* __restrict__ observ;
+    int n, training;
+    uint64_t seed;
+    uint32_t step, env_offset;
+    float* action; float* mean; float* logprob; float* value; float* observ_copy;
+};
+
+// Persistent CTAs; for net in {policy, value}: weights -> shared memory once (TMA), then for every tile of AG_TM envs:
+//   normalise -> layer 1 (O x H1) -> layer 2 (H1 x H2, 4 envs x 4 outputs per thread) -> head (H2 x A | 1) + sampling.
+// blockDim.x = (AG_TM / 4) * (H2 / 4).
+__global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const RexAgentConfig& c = P.D.cfg;
+    const int O = c.obs_dim, A = c.action_dim, H1 = c.hidden1, H2 = c.hidden2;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int wmax = max(P.D.pol_floats, P.D.val_floats);
+    float* W = smem;                          // weights of the current network
+    float* xs = W + wmax;                     // [O][TM] normalised observations
+    float* h1 = xs + AG_MAX_O * AG_TM;        // [H1][TM], reused as [H2][TM] after layer 2
+    float* nrm = h1 + (size_t)H1 * AG_TM;     // [2][O] mean, 1/(std + 1e-8)
+    if (tid == 0) {
+        uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < O) {   // StreamingNormalize.transform constants (normalize.py:57-66, _std :131-144)
+        const int cnt = P.D.cnt[0];
+        float m = P.D.filt[tid], vs = P.D.filt[O + tid];
+        float inv = 1.f;
+        if (cnt > 1) inv = 1.f / (sqrtf(vs / (float)(cnt - 1) + 1e-4f) + 1e-8f);
+        nrm[tid] = m; nrm[O + tid] = inv;
+    }
+    __syncthreads();
+    const int ntiles = (P.n + AG_TM - 1) / AG_TM;
+    const uint32_t step = P.step + (uint32_t)P.D.cnt[2];
+    const int eg = tid % (AG_TM / 4), og = tid / (AG_TM / 4);
+    const bool l2_active = og < H2 / 4;               // the launch rounds the block up to AG_TM threads for tiny networks
+    for (int net = 0; net < 2; net++) {
+        const int AO = net == 0 ? A : 1;
+        const int wfloats = net == 0 ? P.D.pol_floats : P.D.val_floats;
+        __syncthreads();                                   // everyone is done with the previous network's weights
+        tma_bulk_load(W, P.D.params + (net == 0 ? 0 : P.D.pol_floats), (uint32_t)wfloats * 4u, &bar, (uint32_t)net);
+        const float* W1 = W; const float* b1 = W1 + O * H1;
+        const float* W2 = b1 + H1; const float* b2 = W2 + H1 * H2;
+        const float* W3 = b2 + H2; const float* b3 = W3 + H2 * AO;
+        const float* logstd = b3 + AO;                      // policy block only
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int e0 = tile * AG_TM;
+            __syncthreads();                                // previous tile's head is done with h1
+            for (int i = tid; i < AG_TM * O; i += nt) {     // coalesced read of the [TM][O] block
+                const int e = i / O, o = i - e * O;
+                float v = 0.f;
+                if (e0 + e < P.n) {
+                    v = P.observ[(size_t)(e0 + e) * O + o];
+                    if (net == 0 && P.observ_copy) P.observ_copy[(size_t)(e0 + e) * O + o] = v;
+                }
+                v = (v - nrm[o]) * nrm[O + o];
+                v = fminf(fmaxf(v, -c.observ_clip), c.observ_clip);
+                xs[o * AG_TM + e] = v;
+            }
+            __syncthreads();
+            for (int i = tid; i < H1 * AG_TM; i += nt) {    // layer 1
+                const int k = i / AG_TM, e = i - k * AG_TM;
+                float s = b1[k];
+                for (int o = 0; o < O; o++) s = fmaf(xs[o * AG_TM + e], W1[o * H1 + k], s);
+                h1[i] = fmaxf(s, 0.f);
+            }
+            __syncthreads();
+            float acc[4][4];                                // layer 2: 4 envs x 4 outputs per thread
+            if (l2_active) {
+                const float4 bb = ld4(b2 + 4 * og);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+            }
+            const float* hp = h1 + 4 * eg;
+            const float* wp = W2 + 4 * og;
+#pragma unroll 4
+            for (int k = 0; k < (l2_active ? H1 : 0); k++) {
+                const float4 h = ld4(hp + k * AG_TM);
+                const float4 w = ld4(wp + k * H2);
+                acc[0][0] = fmaf(h.x, w.x, acc[0][0]); acc[0][1] = fmaf(h.x, w.y, acc[0][1]); acc[0][2] = fmaf(h.x, w.z, acc[0][2]); acc[0][3] = fmaf(h.x, w.w, acc[0][3]);
+                acc[1][0] = fmaf(h.y, w.x, acc[1][0]); acc[1][1] = fmaf(h.y, w.y, acc[1][1]); acc[1][2] = fmaf(h.y, w.z, acc[1][2]); acc[1][3] = fmaf(h.y, w.w, acc[1][3]);
+                acc[2][0] = fmaf(h.z, w.x, acc[2][0]); acc[2][1] = fmaf(h.z, w.y, acc[2][1]); acc[2][2] = fmaf(h.z, w.z, acc[2][2]); acc[2][3] = fmaf(h.z, w.w, acc[2][3]);
+                acc[3][0] = fmaf(h.w, w.x, acc[3][0]); acc[3][1] = fmaf(h.w, w.y, acc[3][1]); acc[3][2] = fmaf(h.w, w.z, acc[3][2]); acc[3][3] = fmaf(h.w, w.w, acc[3][3]);
+            }
+            __syncthreads();                                // all reads of h1 done: reuse it for h2 [H2][TM]
+#pragma unroll
+            for (int j = 0; j < (l2_active ? 4 : 0); j++) {
+                float4 v = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+                *reinterpret_cast<float4*>(h1 + (4 * og + j) * AG_TM + 4 * eg) = v;
+            }
+            __syncthreads();
+            if (tid < AG_TM && e0 + tid < P.n) {            // head: one thread per env
+                const int e = tid, env = e0 + e;
+                float s[AG_MAX_A];
+#pragma unroll
+                for (int a = 0; a < AG_MAX_A; a++) s[a] = a < AO ? b3[a] : 0.f;
+                for (int k = 0; k < H2; k++) {
+                    const float h = h1[k * AG_TM + e];
+#pragma unroll
+                    for (int a = 0; a < AG_MAX_A; a++) if (a < AO) s[a] = fmaf(h, W3[k * AO + a], s[a]);
+                }
+                if (net == 1) {
+                    if (P.value) P.value[env] = s[0];
+                } else {
+                    float lp = 0.f;
+#pragma unroll
+                    for (int a = 0; a < AG_MAX_A; a++) {
+                        if (a < A) {
+                            const float mu = tanhf(s[a]);
+                            const float ls = logstd[a];
+                            float act = mu, z = 0.f;
+                            if (P.training) {               // network.policy.sample (algorithm.py:116)
+                                const uint32_t genv = P.env_offset + (uint32_t)env;
+                                const float u1 = ((float)(rand_u32(P.seed, genv, step, 2 * a) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                                const float u2 = ((float)(rand_u32(P.seed, genv, step, 2 * a + 1) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                                z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+                                act = fmaf(expf(ls), z, mu);
+                            }
+                            lp += -0.5f * z * z - ls - 0.9189385332046727f;     // diag-normal log-density
+                            if (P.action) P.action[(size_t)env * A + a] = act;
+                            if (P.mean) P.mean[(size_t)env * A + a] = mu;
+                        }
+                    }
+                    if (P.logprob) P.logprob[env] = lp;
+                }
+            }
+        }
+    }
+}
+
+// StreamingNormalize.update for the observation columns and the reward column in one launch (normalize.py:73-99):
+// per column j: S1 = sum(x - mean), S2 = sum((x - mean)^2) over the batch (block partials, then the last block to
+// finish adds them in a fixed order -> bit-reproducible); count += n; new_mean = mean + S1/count;
+// var_sum += S2 - S1^2/count  ( = sum (x - mean)(x - new_mean) ).
+struct ExperienceArgs { AgentDev D; const float* __restrict__ observ; const float* __restrict__ reward; int n; };
+
+__global__ void __launch_bounds__(256) experience_kernel(const ExperienceArgs P) {
+    const int O = P.D.cfg.obs_dim, C = O + 1;
+    __shared__ float red[2 * (AG_MAX_O + 1)][8];
+    __shared__ float mean_s[AG_MAX_O + 1];
+    __shared__ int last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < C) mean_s[tid] = tid < O ? P.D.filt[tid] : P.D.filt[2 * O];
+    __syncthreads();
+    // each thread walks rows with a fixed stride; column sums kept per thread for its own column set
+    for (int cidx = 0; cidx < C; cidx++) {
+        float s1 = 0.f, s2 = 0.f;
+        const float m = mean_s[cidx];
+        for (int e = blockIdx.x * blockDim.x + tid; e < P.n; e += gridDim.x * blockDim.x) {
+            const float x = cidx < O ? P.observ[(size_t)e * O + cidx] : P.reward[e];
+            const float d = x - m;
+            s1 += d; s2 = fmaf(d, d, s2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0) { red[2 * cidx][warp] = s1; red[2 * cidx + 1][warp] = s2; }
+    }
+    __syncthreads();
+    if (tid < 2 * C) {
+        float s = 0.f;
+        for (int w = 0; w < 8; w++) s += red[tid][w];
+        P.D.partial[(size_t)blockIdx.x * 2 * C + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(&P.D.cnt[3], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (tid < C) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int b = 0; b < (int)gridDim.x; b++) {
+            s1 += __ldcg(&P.D.partial[(size_t)b * 2 * C + 2 * tid]);
+            s2 += __ldcg(&P.D.partial[(size_t)b * 2 * C + 2 * tid + 1]);
+        }
+        const int which = tid < O ? 0 : 1;
+        const int cnt = P.D.cnt[which] + P.n;
+        const float step = (float)cnt;
+        float* meanp = tid < O ? &P.D.filt[tid] : &P.D.filt[2 * O];
+        float* varp = tid < O ? &P.D.filt[O + tid] : &P.D.filt[2 * O + 1];
+        float new_mean = *meanp + s1 / step;
+        if (cnt <= 1) new_mean = tid < O ? P.observ[tid] : P.reward[0];     // tf.cond(count > 1, new_mean, value[0])
+        *varp += s2 - s1 * (s1 / step);
+        *meanp = new_mean;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        P.D.cnt[0] += P.n; P.D.cnt[1] += P.n;
+        P.D.cnt[2] += 1;          // device step counter: the next perform draws fresh noise
+        P.D.cnt[3] = 0;
+    }
+}
+
+__global__ void transform_reward_kernel(const AgentDev D, const float* __restrict__ r, int n, float* __restrict__ out) {
+    const int O = D.cfg.obs_dim;
+    const int cnt = D.cnt[1];
+    float inv = 1.f;
+    if (cnt > 1) inv = 1.f / (sqrtf(D.filt[2 * O + 1] / (float)(cnt - 1) + 1e-4f) + 1e-8f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = fminf(fmaxf(r[i] * inv, -D.cfg.reward_clip), D.cfg.reward_clip);      // center=False, scale=True, clip=10
+}
+
+// ---- scans ---------------------------------------------------------------------------------------------------------
+// one thread per episode row, walking backwards in time; rows are laid out by (stride_e, stride_t) so a time-major
+// buffer (stride_e = 1) is read fully coalesced
+template <bool ADV>
+__global__ void __launch_bounds__(256) row_scan_kernel(const float* __restrict__ reward, const float* __restrict__ value,
+                                                       const int32_t* __restrict__ length, int episodes, int L,
+                                                       int64_t se, int64_t st, float discount, float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= episodes) return;
+    const int len = length[e];
+    float agg = 0.f, next_v = 0.f;                           // value[:, 1:] padded with zeros (utility.py:116)
+    for (int t = L - 1; t >= 0; t--) {
+        const int64_t idx = (int64_t)e * se + (int64_t)t * st;
+        const float r = reward[idx];
+        float cur;
+        if (ADV) {
+            const float v = value[idx];
+            cur = (t < len) ? r + discount * next_v - v : 0.f;          // mask * delta
+            next_v = v;
+        } else {
+            cur = (t < len) ? r : 0.f;                                  // mask * reward
+        }
+        agg = cur + discount * agg;
+        out[idx] = agg;
+    }
+}
+
+__global__ void __launch_bounds__(256) gae_segments_kernel(const float* __restrict__ reward, const float* __restrict__ value,
+                                                           const uint8_t* __restrict__ done, int T, int n, float discount,
+                                                           float lambda, float* __restrict__ out_ret, float* __restrict__ out_adv) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float next_v = value[(size_t)T * n + e], ret = next_v, adv = 0.f;
+    for (int t = T - 1; t >= 0; t--) {
+        const size_t idx = (size_t)t * n + e;
+        const float r = reward[idx], v = value[idx];
+        const float nd = done[idx] ? 0.f : 1.f;
+        const float delta = r + discount * next_v * nd - v;
+        adv = delta + discount * lambda * nd * adv;
+        ret = r + discount * nd * ret;
+        if (out_adv) out_adv[idx] = adv;
+        if (out_ret) out_ret[idx] = ret;
+        next_v = v;
+    }
+}
+
+}  // namespace rexsim
+
+using namespace rexsim;
+
+struct RexAgent {
+    AgentDev D;
+    float* d_params = nullptr;
+    float* d_filt = nullptr;
+    int32_t* d_cnt = nullptr;
+    float* d_partial = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+};
+
+static int afail(int code, const char* msg) { set_error(msg); return code; }
+#define ACK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { char b[256]; snprintf(b, sizeof(b), "%s: %s", #x, cudaGetErrorString(_e)); set_error(b); return REXSIM_ERR_CUDA; } } while (0)
+
+static int64_t pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+static int check_cfg(const RexAgentConfig* c) {
+    if (!c) return afail(REXSIM_ERR_INVALID, "null agent config");
+    if (c->obs_dim <= 0 || c->obs_dim > AG_MAX_O || c->action_dim <= 0 || c->action_dim > AG_MAX_A)
+        return afail(REXSIM_ERR_INVALID, "agent: obs_dim must be 1..32 and action_dim 1..8");
+    if (c->hidden1 <= 0 || c->hidden1 > AG_MAX_H1 || c->hidden2 <= 0 || c->hidden2 > AG_MAX_H2 || (c->hidden1 & 3) || (c->hidden2 & 3))
+        return afail(REXSIM_ERR_UNSUPPORTED, "agent: hidden1 <= 256, hidden2 <= 128, both multiples of 4");
+    return REXSIM_OK;
+}
+
+extern "C" {
+
+int64_t rexagent_policy_floats(const RexAgentConfig* c) {
+    if (!c) return 0;
+    const int64_t O = c->obs_dim, A = c->action_dim, H1 = c->hidden1, H2 = c->hidden2;
+    return pad4(O * H1 + H1 + H1 * H2 + H2 + H2 * A + A + A);
+}
+int64_t rexagent_value_floats(const RexAgentConfig* c) {
+    if (!c) return 0;
+    const int64_t O = c->obs_dim, H1 = c->hidden1, H2 = c->hidden2;
+    return pad4(O * H1 + H1 + H1 * H2 + H2 + H2 + 1);
+}
+
+static size_t perform_smem_bytes(const RexAgentConfig* c) {
+    const size_t wmax = (size_t)(rexagent_policy_floats(c) > rexagent_value_floats(c) ? rexagent_policy_floats(c) : rexagent_value_floats(c));
+    return (wmax + (size_t)AG_MAX_O * AG_TM + (size_t)c->hidden1 * AG_TM + 2 * AG_MAX_O) * sizeof(float);
+}
+
+int rexagent_create(const RexAgentConfig* cfg, RexAgent** out) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!out) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (perform_smem_bytes(cfg) > 227 * 1024) return afail(REXSIM_ERR_UNSUPPORTED, "agent: network does not fit the 227 KB of shared memory");
+    RexAgent* a = new RexAgent();
+    a->D.cfg = *cfg;
+    a->D.pol_floats = (int)rexagent_policy_floats(cfg); a->D.val_floats = (int)rexagent_value_floats(cfg);
+    const size_t np = (size_t)a->D.pol_floats + a->D.val_floats;
+    const int O = cfg->obs_dim;
+    int dev = 0;
+    ACK(cudaGetDevice(&dev));
+    ACK(cudaDeviceGetAttribute(&a->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    ACK(cudaMalloc(&a->d_params, np * sizeof(float)));
+    ACK(cudaMemset(a->d_params, 0, np * sizeof(float)));
+    ACK(cudaMalloc(&a->d_filt, (2 * O + 2) * sizeof(float)));
+    ACK(cudaMemset(a->d_filt, 0, (2 * O + 2) * sizeof(float)));
+    ACK(cudaMalloc(&a->d_cnt, 4 * sizeof(int32_t)));
+    ACK(cudaMemset(a->d_cnt, 0, 4 * sizeof(int32_t)));
+    ACK(cudaMalloc(&a->d_partial, (size_t)RED_BLOCKS * 2 * (O + 1) * sizeof(float)));
+    ACK(cudaFuncSetAttribute(perform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_smem_bytes(cfg)));
+    a->D.params = a->d_params; a->D.filt = a->d_filt; a->D.cnt = a->d_cnt; a->D.partial = a->d_partial;
+    ACK(cudaDeviceSynchronize());
+    *out = a;
+    return REXSIM_OK;
+}
+void rexagent_destroy(RexAgent* a) {
+    if (!a) return;
+    cudaFree(a->d_params); cudaFree(a->d_filt); cudaFree(a->d_cnt); cudaFree(a->d_partial);
+    delete a;
+}
+int rexagent_set_params(RexAgent* a, const float* h, int64_t n) {
+    if (!a || !h) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n != (int64_t)a->D.pol_floats + a->D.val_floats) return afail(REXSIM_ERR_INVALID, "agent: parameter block size mismatch");
+    ACK(cudaMemcpy(a->d_params, h, n * sizeof(float), cudaMemcpyHostToDevice));
+    return REXSIM_OK;
+}
+int rexagent_get_params(RexAgent* a, float* h, int64_t n) {
+    if (!a || !h) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n != (int64_t)a->D.pol_floats + a->D.val_floats) return afail(REXSIM_ERR_INVALID, "agent: parameter block size mismatch");
+    ACK(cudaMemcpy(h, a->d_params, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return REXSIM_OK;
+}
+int rexagent_params_buffer(RexAgent* a, float** p) {
+    if (!a || !p) return afail(REXSIM_ERR_INVALID, "null argument");
+    *p = a->d_params;
+    return REXSIM_OK;
+}
+int rexagent_set_filters(RexAgent* a, int32_t oc, const float* om, const float* ov, int32_t rc, float rm, float rv) {
+    if (!a || !om || !ov) return afail(REXSIM_ERR_INVALID, "null argument");
+    const int O = a->D.cfg.obs_dim;
+    std::vector<float> f(2 * O + 2);
+    for (int i = 0; i < O; i++) { f[i] = om[i]; f[O + i] = ov[i]; }
+    f[2 * O] = rm; f[2 * O + 1] = rv;
+    int32_t c[4] = {oc, rc, 0, 0};
+    ACK(cudaMemcpy(a->d_filt, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ACK(cudaMemcpy(a->d_cnt, c, sizeof(c), cudaMemcpyHostToDevice));
+    return REXSIM_OK;
+}
+int rexagent_get_filters(RexAgent* a, int32_t* counts, float* om, float* ov, float* rmv) {
+    if (!a || !counts || !om || !ov || !rmv) return afail(REXSIM_ERR_INVALID, "null argument");
+    const int O = a->D.cfg.obs_dim;
+    std::vector<float> f(2 * O + 2);
+    int32_t c[4];
+    ACK(cudaMemcpy(f.data(), a->d_filt, f.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    ACK(cudaMemcpy(c, a->d_cnt, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < O; i++) { om[i] = f[i]; ov[i] = f[O + i]; }
+    rmv[0] = f[2 * O]; rmv[1] = f[2 * O + 1];
+    counts[0] = c[0]; counts[1] = c[1];
+    return REXSIM_OK;
+}
+
+int rexagent_perform(RexAgent* a, const float* observ, int32_t n, int32_t training, uint64_t seed, uint32_t step,
+                     uint32_t env_offset, float* action, float* mean, float* logprob, float* value, float* observ_copy,
+                     void* stream) {
+    if (!a || !observ) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n <= 0) return afail(REXSIM_ERR_INVALID, "agent: n must be positive");
+    PerformArgs P;
+    P.D = a->D; P.observ = observ; P.n = n; P.training = training; P.seed = seed; P.step = step; P.env_offset = env_offset;
+    P.action = action; P.mean = mean; P.logprob = logprob; P.value = value; P.observ_copy = observ_copy;
+    const int ntiles = (n + AG_TM - 1) / AG_TM;
+    const int blocks = ntiles < a->sm_count ? ntiles : a->sm_count;
+    const int threads = (AG_TM / 4) * (a->D.cfg.hidden2 / 4);
+    perform_kernel<<<blocks, threads < AG_TM ? AG_TM : threads, perform_smem_bytes(&a->D.cfg), (cudaStream_t)stream>>>(P);
+    ACK(cudaGetLastError());
+    a->launches++;
+    return REXSIM_OK;
+}
+int rexagent_experience(RexAgent* a, const float* observ, const float* reward, int32_t n, void* stream) {
+    if (!a || !observ || !reward) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n <= 0) return afail(REXSIM_ERR_INVALID, "agent: n must be positive");
+    ExperienceArgs P; P.D = a->D; P.observ = observ; P.reward = reward; P.n = n;
+    int blocks = (n + 255) / 256;
+    if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+    experience_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    ACK(cudaGetLastError());
+    a->launches++;
+    return REXSIM_OK;
+}
+int rexagent_transform_reward(RexAgent* a, const float* reward, int32_t n, float* out, void* stream) {
+    if (!a || !reward || !out) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n <= 0) return REXSIM_OK;
+    int blocks = (n + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    transform_reward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a->D, reward, n, out);
+    ACK(cudaGetLastError());
+    a->launches++;
+    return REXSIM_OK;
+}
+int rexagent_discounted_return(const float* reward, const int32_t* length, int32_t episodes, int32_t L, int64_t se, int64_t st,
+                               float discount, float* out, void* stream) {
+    if (!reward || !length || !out) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (episodes <= 0 || L <= 0) return afail(REXSIM_ERR_INVALID, "agent: empty scan");
+    row_scan_kernel<false><<<(episodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reward, nullptr, length, episodes, L, se, st, discount, out);
+    ACK(cudaGetLastError());
+    return REXSIM_OK;
+}
+int rexagent_lambda_advantage(const float* reward, const float* value, const int32_t* length, int32_t episodes, int32_t L,
+                              int64_t se, int64_t st, float discount, float* out, void* stream) {
+    if (!reward || !value || !length || !out) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (episodes <= 0 || L <= 0) return afail(REXSIM_ERR_INVALID, "agent: empty scan");
+    row_scan_kernel<true><<<(episodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reward, value, length, episodes, L, se, st, discount, out);
+    ACK(cudaGetLastError());
+    return REXSIM_OK;
+}
+int rexagent_gae_segments(const float* reward, const float* value, const uint8_t* done, int32_t T, int32_t n, float discount,
+                          float lambda, float* out_return, float* out_advantage, void* stream) {
+    if (!reward || !value || !done) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (T <= 0 || n <= 0) return afail(REXSIM_ERR_INVALID, "agent: empty scan");
+    gae_segments_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reward, value, done, T, n, discount, lambda, out_return, out_advantage);
+    ACK(cudaGetLastError());
+    return REXSIM_OK;
+}
+int64_t rexagent_launch_count(const RexAgent* a) { return a ? a->launches : 0; }
+
+}  // extern "C"

@@ -33,6 +33,7 @@ struct RexSim {
 };
 
 static thread_local char g_err[512] = "";
+namespace rexsim { void set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); } }   // shared with rexsim_agent.cu
 static int fail(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
 static int cuda_fail(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));

@@ -338,14 +338,15 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     if (ARM && leg == 0) arm_outward(AR, a0, dt);
 
     // ---- contact candidates: ONE contact per group = its deepest sample point (same groups/order as the oracle) ----
-    //   foot group  (own lane): foot box corners, then toe hull support points (1 mm margin)
+    //   foot group  (own lane): foot box corners, then the toe hull (exact prism support, toe_margin = 0)
     //   upper group (own lane): shoulder box corners, then leg box corners
     //   base group  (owned by lane 0): base + chassis box corners, searched 6 per lane
     float best = 1e30f; V3 rc = mk(0.f, 0.f, 0.f), nrm = mk(0.f, 0.f, 1.f);
     float bestU = 1e30f; V3 rcU = mk(0.f, 0.f, 0.f), nrmU = mk(0.f, 0.f, 1.f); int kU = 1;
     float bestB = 1e30f; V3 rcB = mk(0.f, 0.f, 0.f), nrmB = mk(0.f, 0.f, 1.f);
     const float* BXl = sm + REXSIM_MT_BOX + leg * 72;
-    const float* TPl = sm + REXSIM_MT_TOE + leg * (REXSIM_MAX_TOE_PTS * 3);
+    const float* TPl = sm + REXSIM_MT_TOE;          // [npts][2] (x, z) profile of the toe prism, foot frame
+    const float toe_w = sm[REXSIM_MT_BASE + 15];     // prism half width along y
     const float* BBl = sm + REXSIM_MT_BASEBOX;
     const int npts = P.cfg.toe_npts;
     int jb = 0;
@@ -364,14 +365,22 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 if (d < best) { best = d; jf = j; }
             }
         }
-#pragma unroll 3
-        for (int j = 0; j < npts; j++) {
-            float d = dot(z3, mk(TPl[3 * j], TPl[3 * j + 1], TPl[3 * j + 2])) - P.cfg.toe_margin;
-            if (d < best) { best = d; jf = 8 + j; }
+        {
+            // toe prism: the deepest hull vertex is the profile vertex minimising z3.x*x + z3.z*z on the y face that
+            // minimises z3.y*y (exact support function of the hull: 2 FMA per profile vertex)
+            float bt = 1e30f; int jt = 0;
+#pragma unroll 4
+            for (int j = 0; j < npts; j++) {
+                float d = fmaf(z3.x, TPl[2 * j], z3.z * TPl[2 * j + 1]);
+                if (d < bt) { bt = d; jt = j; }
+            }
+            bt -= fabsf(z3.y) * toe_w + P.cfg.toe_margin;
+            if (bt < best) { best = bt; jf = 8 + jt; }
         }
         {
-            const float* q = jf < 8 ? BXl + 48 + 3 * jf : TPl + 3 * (jf - 8);
-            rc = p3 + mul(R3, mk(q[0], q[1], q[2]));
+            const V3 q = jf < 8 ? mk(BXl[48 + 3 * jf], BXl[48 + 3 * jf + 1], BXl[48 + 3 * jf + 2])
+                                : mk(TPl[2 * (jf - 8)], z3.y > 0.f ? -toe_w : (z3.y < 0.f ? toe_w : -toe_w), TPl[2 * (jf - 8) + 1]);
+            rc = p3 + mul(R3, q);
             best += p3.z + L.pos.z;
         }
         if (zs < 0.05f || zl < 0.12f) {
@@ -411,14 +420,19 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
             if (d < best) { best = d; rc = r; nrm = n; }
         }
+        // heightfield: every 4th profile vertex (+ the last one) on both faces of the prism, same subset as the oracle
 #pragma unroll 1
-        for (int j = 0; j < npts; j++) {
-            V3 r = p3 + mul(R3, mk(TPl[3 * j], TPl[3 * j + 1], TPl[3 * j + 2]));
-            float d; V3 n;
-            if (r.z + L.pos.z > 0.06f) continue;
-            ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
-            d -= P.cfg.toe_margin;
-            if (d < best) { best = d; rc = r; nrm = n; }
+        for (int side = 0; side < 2; side++) {
+#pragma unroll 1
+            for (int j = 0; j < npts; j = (j + 4 < npts || j == npts - 1) ? j + 4 : npts - 1) {
+                V3 r = p3 + mul(R3, mk(TPl[2 * j], side ? toe_w : -toe_w, TPl[2 * j + 1]));
+                float d; V3 n;
+                if (r.z + L.pos.z <= 0.06f) {
+                    ground_query<TERRAIN>(G, mk(r.x + L.pos.x, r.y + L.pos.y, r.z + L.pos.z), d, n);
+                    d -= P.cfg.toe_margin;
+                    if (d < best) { best = d; rc = r; nrm = n; }
+                }
+            }
         }
 #pragma unroll 1
         for (int j = 0; j < 16; j++) {

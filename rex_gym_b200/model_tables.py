@@ -9,8 +9,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 MT_BASE, MT_LEG, MT_TOE, MT_BOX, MT_BASEBOX, MT_FLOATS = 0, 16, 208, 592, 880, 952
 MT_ARM, ARM_STRIDE, MT_FLOATS_ARM = 952, 32, 952 + 192
-MAX_TOE_PTS = 32
-TOE_MARGIN = 0.001   # Bullet's URDF importer puts a 1 mm collision margin on convex hulls
+MAX_TOE_PTS = 96     # profile vertices of the toe prism ((x, z) pairs: 2 * 96 floats fit the 384-float toe block)
+# margin added to the toe hull's reach: 0 -- the PyBullet trajectories recovered from the reference's checkpoints put the
+# touchdown where the exact hull WITHOUT Bullet's 1 mm importer margin reaches the ground (tools/dev_pybullet_replay.py)
+TOE_MARGIN = 0.0
 
 
 def _rpy_to_mat(rpy):
@@ -84,15 +86,25 @@ def pack_model_tables(mark="base"):
             t[ob:ob + 24] = np.asarray(box[0]["points"]).reshape(-1)
             hull = [s for s in b["shapes"] if s["kind"] == "hull"]
             if bi == 2:
-                if len(hull) != 1:
-                    raise ValueError("expected one toe hull on the foot body")
+                # the toe is a prism (tools/compile_urdf.py support_polytope): a convex (x, z) profile extruded over
+                # y in [-w, +w] in the foot body frame, identical on the four feet -> one shared [npts][2] profile + w
+                if len(hull) != 1 or "prism_profile_points" not in hull[0]:
+                    raise ValueError("expected one prism toe hull on the foot body")
                 pts = np.asarray(hull[0]["points"])
+                n = int(hull[0]["prism_profile_points"])
+                lo, hi = pts[:n], pts[n:]
+                if len(pts) != 2 * n or n > MAX_TOE_PTS or not np.allclose(lo[:, [0, 2]], hi[:, [0, 2]], atol=1e-12):
+                    raise ValueError("toe hull is not a prism of <= %d profile vertices" % MAX_TOE_PTS)
+                w = float(hi[0, 1])
+                if not (np.allclose(lo[:, 1], -w, atol=1e-9) and np.allclose(hi[:, 1], w, atol=1e-9) and w > 0):
+                    raise ValueError("toe prism must be centred on y = 0 in the foot frame")
+                prof = lo[:, [0, 2]]
                 if npts is None:
-                    npts = len(pts)
-                if len(pts) != npts or npts > MAX_TOE_PTS:
-                    raise ValueError("toe hulls must have the same number (<=32) of sample points")
-                ot = MT_TOE + 3 * MAX_TOE_PTS * leg
-                t[ot:ot + 3 * npts] = pts.reshape(-1)
+                    npts, prof0, w0 = n, prof, w
+                    t[MT_TOE:MT_TOE + 2 * n] = prof.reshape(-1)
+                    t[MT_BASE + 15] = w            # toe half width (the pad word of the base block)
+                elif n != npts or not np.allclose(prof, prof0, atol=1e-12) or abs(w - w0) > 1e-12:
+                    raise ValueError("the four toe hulls must be identical in their foot frames")
     if arm:
         for k in range(6):
             b = bodies[13 + k]

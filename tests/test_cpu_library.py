@@ -68,14 +68,16 @@ def test_model_table_packer_layout():
     from rex_gym_b200.model_tables import pack_model_tables, MT_LEG, MT_TOE, MT_BOX, MT_BASEBOX, MT_FLOATS
     t, npts = pack_model_tables("base")
     assert t.dtype == np.float32 and t.shape == (MT_FLOATS,) and MT_FLOATS * 4 % 16 == 0   # TMA bulk copy granularity
-    assert npts == 27
+    assert npts == 68                                # profile vertices of the toe prism (exact hull of stl/foot.stl, curved part)
     assert abs(t[0] - 1.3) < 1e-6 and abs(t[10] - 1.2) < 1e-6                             # merged base / un-merged root mass
     legs = t[MT_LEG:MT_LEG + 192].reshape(4, 3, 16)
     np.testing.assert_allclose(legs[:, 0, :3], [[-0.093, -0.036, 0], [-0.093, 0.036, 0], [0.093, -0.036, 0], [0.093, 0.036, 0]], atol=1e-7)
     np.testing.assert_allclose(legs[:, 1, 3], 0.6, atol=1e-6)                            # leg link + 0.5 kg cover (rex.urdf)
     np.testing.assert_allclose(legs[:, 2, 7], -0.1, atol=1e-6); np.testing.assert_allclose(legs[:, 2, 14], 2.59, atol=1e-6)
-    toe = t[MT_TOE:MT_TOE + 384].reshape(4, 32, 3)
-    assert np.all(toe[:, npts:] == 0) and np.all(np.abs(toe[:, :npts]).max(axis=(1, 2)) < 0.16)
+    toe = t[MT_TOE:MT_TOE + 384].reshape(192, 2)         # (x, z) profile in the foot frame, shared by the four feet
+    assert np.all(toe[npts:] == 0) and np.all(np.abs(toe[:npts, 0]) < 0.02) and np.all(toe[:npts, 1] < -0.10)
+    assert abs(toe[:npts, 1].min() + 0.13444) < 1e-4                                        # lowest hull point: 134.4 mm below the knee
+    assert abs(t[15] - 0.01) < 1e-7                                                         # prism half width
     assert t[MT_BOX:MT_BASEBOX].reshape(4, 3, 8, 3).shape == (4, 3, 8, 3)
 
 

@@ -376,3 +376,45 @@ def test_single_env_facade_matches_the_reference_signatures():
     assert env.env_step_counter == 20 and abs(env.rex.GetTimeSinceReset() - 0.1) < 1e-9
     assert env.action_space.shape == (2,) and env.observation_space.shape == (4,)
     env.close()
+
+
+@pytest.mark.parametrize("task", ["gallop", "walk"])
+def test_cuda_path_tracks_pybullet_goldens(task):
+    """The CUDA path against REAL PyBullet trajectories recovered from the reference's checkpoints (see
+    tests/test_pybullet_goldens.py for the fixture and the oracle's numbers): the 12 recorded episodes run as one batch
+    from the pristine pose, stored policy actions in, RangeNormalize'd observations out, same bounds as the oracle."""
+    import math
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pybullet_memory_golden.npz"))
+    ua, ur = 2 * math.pi + 0.01, 2 * math.pi / 0.001 + 0.01
+
+    def denorm(o):
+        o = np.array(o, np.float64)
+        o[..., 0:2] *= ua; o[..., 2:4] *= ur; o[..., 4:] *= ua
+        return o
+    n, steps = 12, 150
+    ac, ref = G[task + "_ol_action"][:n], denorm(G[task + "_ol_observ"][:n])
+    kw = dict(target_position=2.0) if task == "gallop" else dict(target_position=2.0, backwards=False)
+    env = _env(task, n, signal_type="ol", normalize=True, **kw)
+    env.reset()
+    ol = np.array([0.15192765, -0.90412283, 1.48156545])
+    q0 = np.tile(np.concatenate([ol * [s, 1, 1] for s in (1, -1, 1, -1)]), (n, 1))
+    env.set_state(np.tile([0, 0, 0.21], (n, 1)), np.tile([0, 0, 0, 1], (n, 1)), np.zeros((n, 3)), np.zeros((n, 3)), q0, np.zeros((n, 12)))
+    rp, q = np.zeros((n, steps)), np.zeros((n, steps))
+    for t in range(steps):
+        o, r, d, _ = env.step(ac[:, t])
+        o = denorm(o)
+        rp[:, t] = np.abs(o[:, 0:2] - ref[:, t + 1, 0:2]).max(1)
+        if o.shape[1] > 4:
+            q[:, t] = np.abs(o[:, 4:] - ref[:, t + 1, 4:]).max(1)
+        assert not d.any()
+    if task == "gallop":
+        assert np.median(q[:, 0]) < 5e-4 and np.median(q[:, 1]) < 1.2e-3
+        assert np.median(q[:, :20].max(1)) < 1.1e-2 and np.median(rp[:, :20].max(1)) < 5e-3
+        assert np.median(q.max(1)) < 3.5e-2 and np.median(rp.max(1)) < 1.6e-2
+        assert np.median(q.mean(1)) < 8.5e-3 and np.median(rp.mean(1)) < 5e-3
+    else:
+        assert np.median(rp[:, :5].max(1)) < 5e-4
+        assert np.median(rp.max(1)) < 4.5e-3 and np.median(rp.mean(1)) < 1.5e-3
+    assert env.check_errors() == 0
+    env.close()

@@ -116,7 +116,8 @@ def test_friction_cone_holds_a_standing_robot_against_a_small_push():
 def test_heightfield_flat_equals_plane():
     flat = np.zeros((1, 256, 256), np.float32)
     a = OracleSim(1, "walk", target_position=2.0, backwards=False)
-    b = OracleSim(1, "walk", terrain="random", fields=flat, target_position=2.0, backwards=False)
+    # terrain_full_toe: sample every toe hull vertex on the heightfield too (the product samples every 4th one there)
+    b = OracleSim(1, "walk", terrain="random", fields=flat, target_position=2.0, backwards=False, terrain_full_toe=True)
     b.cfg.friction = a.cfg.friction
     b.L.rexo_destroy(b.h); b.h = b.L.rexo_create(C.byref(b.model), C.byref(b.cfg))
     a.reset(); b.reset()

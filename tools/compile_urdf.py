@@ -57,19 +57,20 @@ def load_stl_vertices(path, scale):
 
 
 def support_polytope(verts):
-    """K-point support subset of the toe hull: extreme vertices along a fan of
-    directions over the curved (z<=0 in mesh frame) half of the tyre profile."""
+    """Exact support set of the toe hull.  stl/foot.stl is a prism: a convex 2-D profile in the mesh x-z plane extruded
+    along y (672 y-layers of the same tyre profile).  Its convex hull is therefore {profile hull vertices} x {y_min, y_max}:
+    74 profile vertices; the ones on the flat top (mesh z == 0) can never be the deepest point against a ground below the
+    robot and are dropped, leaving the curved part.  Every retained vertex is a true hull vertex, so the support function
+    (deepest point along any downward direction) is exact -- an earlier 27-point subset under-estimated the reach by up
+    to 0.4 mm between samples, which PyBullet trajectories recovered from the reference's checkpoints exposed as a
+    touchdown that came one control step late (tools/dev_pybullet_replay.py)."""
     from scipy.spatial import ConvexHull
-    hv = verts[ConvexHull(verts).vertices]
-    c = 0.5 * (hv.min(0) + hv.max(0))
-    picks = []
-    thetas = np.linspace(-np.pi, 0.0, 9)
-    for phi in np.deg2rad([-55.0, 0.0, 55.0]):
-        for th in thetas:
-            d = np.array([np.cos(th) * np.cos(phi), np.sin(phi), np.sin(th) * np.cos(phi)])
-            picks.append(int(np.argmax((hv - c) @ d)))
-    idx = sorted(set(picks))
-    return hv[idx]
+    xz = verts[:, [0, 2]]
+    prof = xz[ConvexHull(xz).vertices]
+    prof = prof[prof[:, 1] < -1e-4]                                  # drop the flat top edge
+    prof = prof[np.argsort(np.arctan2(prof[:, 1], prof[:, 0]))]      # ordered along the arc
+    y0, y1 = verts[:, 1].min(), verts[:, 1].max()
+    return np.array([[x, y, z] for y in (y0, y1) for x, z in prof])
 
 
 def parse_urdf(path, stl_dir):
@@ -183,6 +184,8 @@ def compile_model(urdf_path, stl_dir, motor_names):
             for sh in lk["shapes"]:
                 shapes.append(dict(link=lk["name"], kind=sh["kind"],
                                    points=(shape_points(sh) @ R.T + t).tolist()))
+                if sh["kind"] == "hull":     # prism: first half = profile on the y_min face, second half = y_max face
+                    shapes[-1]["prism_profile_points"] = len(shapes[-1]["points"]) // 2
         b = dict(name=link_name, parent=parent_body, mass=mass, com=com.tolist(), inertia=I.tolist(),
                  shapes=shapes, links=[p[0]["name"] for p in parts])
         if joint is not None:

@@ -1,0 +1,51 @@
+#!/usr/bin/env python3
+"""Recover REAL PyBullet trajectories from the reference's shipped PPO checkpoints and commit them as golden fixtures.
+
+Every checkpoint under /root/reference/rex_gym/policies/<task>/<signal>/ stores, next to the network weights, the PPO
+EpisodeMemory variables (rex_gym/agents/ppo/memory.py:32-45; algorithm.py:59-62): `memory/Variable_1..5` = the observations,
+actions, action means, log-stddevs and rewards of the last `update_every` training episodes, recorded by the reference's
+own RexGymEnv on pybullet==2.8.3 behind its training wrappers (ClipAction / RangeNormalize / ConvertTo32Bit,
+rex_gym/agents/scripts/utility.py).  `EpisodeMemory.clear` only zeroes the length vector, so the rows survive in the file.
+
+For the OPEN-LOOP tasks the motor command depends only on the action and the simulation clock (gallop_env.py:286-304,
+walk_env.py:292-315, turn_env.py:271-311) -- no wall-clock gait phase -- so replaying the stored actions from the stored
+initial observation is a like-for-like test of pybullet.stepSimulation + the motor model, the part of the hot path whose
+parity could not be pinned any other way (pybullet is not installable here).
+
+Output: tests/golden/pybullet_memory_golden.npz  (first STEPS control steps of EPISODES episodes per task; float32 as stored).
+  <task>_<signal>_action [E][K][A]    policy output, before ClipAction / denormalisation (wrappers.py:218-265)
+  <task>_<signal>_observ [E][K+1][O]  RangeNormalize'd observation BEFORE each step (row 0 = reset observation)
+  <task>_<signal>_reward [E][K]
+The reader is rex_gym_b200/agents/tf_checkpoint.py (pure Python; TensorFlow is not needed).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from rex_gym_b200.agents import tf_checkpoint as tfc  # noqa: E402
+
+REF = "/root/reference/rex_gym/policies"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "pybullet_memory_golden.npz")
+TASKS = [("gallop", "ol"), ("walk", "ol"), ("turn", "ol"), ("standup", "ol")]
+EPISODES, STEPS = 12, 160
+
+
+def main():
+    out = {}
+    for task, sig in TASKS:
+        prefix = tfc.latest_checkpoint(os.path.join(REF, task, sig))
+        v = tfc.load_variables(prefix, ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
+        ob, ac, rw = v["memory/Variable_1"], v["memory/Variable_2"], v["memory/Variable_5"]
+        name = "%s_%s" % (task, sig)
+        out[name + "_action"] = ac[:EPISODES, :STEPS].astype(np.float32)
+        out[name + "_observ"] = ob[:EPISODES, :STEPS + 1].astype(np.float32)
+        out[name + "_reward"] = rw[:EPISODES, :STEPS].astype(np.float32)
+        print(name, os.path.basename(prefix), "memory", ob.shape, "->", out[name + "_observ"].shape)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()
