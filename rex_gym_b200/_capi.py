@@ -26,6 +26,16 @@ class RexSimConfig(C.Structure):
     ]
 
 
+class RexAgentConfig(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("hidden1", C.c_int32), ("hidden2", C.c_int32),
+                ("observ_clip", C.c_float), ("reward_clip", C.c_float)]
+
+
+AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_create", "rexagent_destroy", "rexagent_set_params",
+                 "rexagent_get_params", "rexagent_params_buffer", "rexagent_set_filters", "rexagent_get_filters",
+                 "rexagent_perform", "rexagent_experience", "rexagent_transform_reward", "rexagent_discounted_return",
+                 "rexagent_lambda_advantage", "rexagent_gae_segments", "rexagent_launch_count"]
+
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
            "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
            "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
@@ -67,6 +77,24 @@ def load():
     L.rexsim_last_error.restype = C.c_char_p
     L.rexsim_rand_u32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rexsim_rand_u32.restype = C.c_uint32
+    # include/rexsim_agent.h
+    cfgp = C.POINTER(RexAgentConfig)
+    L.rexagent_policy_floats.argtypes = [cfgp]; L.rexagent_policy_floats.restype = C.c_int64
+    L.rexagent_value_floats.argtypes = [cfgp]; L.rexagent_value_floats.restype = C.c_int64
+    L.rexagent_create.argtypes = [cfgp, C.POINTER(C.c_void_p)]
+    L.rexagent_destroy.argtypes = [C.c_void_p]; L.rexagent_destroy.restype = None
+    L.rexagent_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.rexagent_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.rexagent_params_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rexagent_set_filters.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float]
+    L.rexagent_get_filters.argtypes = [C.c_void_p] * 5
+    L.rexagent_perform.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32] + [C.c_void_p] * 6
+    L.rexagent_experience.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.rexagent_transform_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.rexagent_discounted_return.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    L.rexagent_lambda_advantage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    L.rexagent_gae_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rexagent_launch_count.argtypes = [C.c_void_p]; L.rexagent_launch_count.restype = C.c_int64
     _LIB = L
     return L
 

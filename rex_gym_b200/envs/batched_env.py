@@ -228,6 +228,12 @@ class BatchedRexEnv(object):
             raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
         return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), _Info(self)
 
+    def step_into(self, action, obs, reward, done_u8):
+        """Raw device form of step(): CUDA float32 action [N][A] in; obs [N][O], reward [N] (float32) and done [N] (uint8) are
+        written into the caller's contiguous CUDA buffers (e.g. slices of a rollout).  One asynchronous kernel launch."""
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.rexsim_step(self._h, action.data_ptr(), obs.data_ptr(), reward.data_ptr(), done_u8.data_ptr(), self._stream()))
+
     def reset(self, indices=None):
         """BatchEnv.reset (batch_env.py:92-109): observations of the reset environments."""
         with torch.cuda.device(self.device):
