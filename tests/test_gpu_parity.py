@@ -162,8 +162,9 @@ def test_free_running_rollout(task, sig, kw):
             ocmd = np.stack([np.array(ora.env(i).cmd[:12]) for i in range(n)])
             assert np.abs(cmd - ocmd)[cmp].max() < 5e-4, f"cmd step {k}"    # controller half: fp32 IK/Bezier vs fp64
             rcmp = cmp.copy()
-            if task == "standup":      # the standup reward jumps by 1 where the base crosses z = 0.21 (standup_env.py:163-165)
-                rcmp &= np.abs(so["pos"][:, 2] - 0.21) > 2e-3
+            if task == "standup":      # the standup reward jumps by 1 where the base crosses z = 0.21 or the L1 distance 0.1 (standup_env.py:151-167)
+                l1 = np.abs(so["pos"][:, 0]) + np.abs(so["pos"][:, 1]) + np.abs(0.21 - so["pos"][:, 2])
+                rcmp &= (np.abs(so["pos"][:, 2] - 0.21) > 2e-3) & (np.abs(l1 - 0.1) > 2e-3)
             np.testing.assert_allclose(rg[rcmp], rc[rcmp], atol=5e-3)
         else:
             assert np.median(eq) < 2 * tol_q and np.median(ep) < 2 * tol_p, f"step {k}"
