@@ -57,6 +57,10 @@ int rexagent_set_filters(RexAgent* a, int32_t observ_count, const float* observ_
 int rexagent_get_filters(RexAgent* a, int32_t* counts /*[2]*/, float* observ_mean, float* observ_var_sum,
                          float* reward_mean_var /*[2]*/);
 
+/* raw device state for checkpoint / resume: filt dev [2*O + 2] f32 (observ mean[O], var_sum[O], reward mean, var_sum);
+ * counters dev [4] i32 (observ count, reward count, step counter, internal ticket = 0 between launches) */
+int rexagent_state_buffers(RexAgent* a, float** filt, int32_t** counters);
+
 /* observ dev [n][O] -> action dev [n][A], mean dev [n][A], logprob dev [n], value dev [n]  (any output may be NULL).
  * training != 0: action = mean + exp(logstd) * eps, eps ~ N(0,1) from the counter-based generator keyed on
  * (seed, env_offset + env, step + device step counter, action index); training == 0: action = mean.

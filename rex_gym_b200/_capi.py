@@ -32,7 +32,7 @@ class RexAgentConfig(C.Structure):
 
 
 AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_create", "rexagent_destroy", "rexagent_set_params",
-                 "rexagent_get_params", "rexagent_params_buffer", "rexagent_set_filters", "rexagent_get_filters",
+                 "rexagent_get_params", "rexagent_params_buffer", "rexagent_state_buffers", "rexagent_set_filters", "rexagent_get_filters",
                  "rexagent_perform", "rexagent_experience", "rexagent_transform_reward", "rexagent_discounted_return",
                  "rexagent_lambda_advantage", "rexagent_gae_segments", "rexagent_launch_count"]
 
@@ -86,6 +86,7 @@ def load():
     L.rexagent_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.rexagent_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.rexagent_params_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rexagent_state_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rexagent_set_filters.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float]
     L.rexagent_get_filters.argtypes = [C.c_void_p] * 5
     L.rexagent_perform.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32] + [C.c_void_p] * 6

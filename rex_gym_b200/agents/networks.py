@@ -44,6 +44,11 @@ class ForwardGaussianPolicy(object):
         with torch.cuda.device(self.device):
             _capi.check(self._L.rexagent_create(C.byref(c), C.byref(h)))
         self._h = h
+        pf, pc = C.c_void_p(), C.c_void_p()
+        _capi.check(self._L.rexagent_state_buffers(self._h, C.byref(pf), C.byref(pc)))
+        from ..envs.batched_env import _DevArray
+        self._filt = torch.as_tensor(_DevArray(pf.value, (2 * self.O + 2,), "<f4", self), device=self.device)
+        self._cnt = torch.as_tensor(_DevArray(pc.value, (4,), "<i4", self), device=self.device)
         self.observ_filter = StreamingNormalize(self, "observ")
         self.reward_filter = StreamingNormalize(self, "reward")
         # initialisers of networks.py:18-19 and tf.contrib.layers defaults: xavier-uniform hidden layers, zero biases,
@@ -159,6 +164,13 @@ class ForwardGaussianPolicy(object):
         with torch.cuda.device(self.device):
             _capi.check(self._L.rexagent_transform_reward(self._h, reward.data_ptr(), reward.numel(), out.data_ptr(), self._stream()))
         return out
+
+    def state_dict(self):
+        """Filter statistics and counters (device tensors): with get_weights() the complete agent state."""
+        return {"filters": self._filt.clone(), "counters": self._cnt.clone()}
+
+    def load_state_dict(self, sd):
+        self._filt.copy_(sd["filters"]); self._cnt.copy_(sd["counters"])
 
     @property
     def launch_count(self):

@@ -60,9 +60,14 @@ class Rollout(object):
                 torch.cuda.synchronize(self.env.device)
                 side = torch.cuda.Stream(device=self.env.device)
                 side.wait_stream(torch.cuda.current_stream(self.env.device))
+                # warm-up outside capture (lazy kernel loading must not happen while capturing); the warm-up advances the
+                # environments and the filters, so everything is snapshotted first and put back afterwards
+                snap = (self.env.state_dict(), self.net.state_dict(), self._cur.clone())
                 with torch.cuda.stream(side):
-                    self._loop()                               # warm-up outside capture (lazy module loading etc.)
+                    self._loop()
                 torch.cuda.current_stream(self.env.device).wait_stream(side)
+                torch.cuda.synchronize(self.env.device)
+                self.env.load_state_dict(snap[0]); self.net.load_state_dict(snap[1]); self._cur.copy_(snap[2])
                 torch.cuda.synchronize(self.env.device)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):

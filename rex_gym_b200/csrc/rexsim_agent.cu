@@ -390,6 +390,12 @@ int rexagent_params_buffer(RexAgent* a, float** p) {
     *p = a->d_params;
     return REXSIM_OK;
 }
+int rexagent_state_buffers(RexAgent* a, float** filt, int32_t** counters) {
+    if (!a) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (filt) *filt = a->d_filt;
+    if (counters) *counters = a->d_cnt;
+    return REXSIM_OK;
+}
 int rexagent_set_filters(RexAgent* a, int32_t oc, const float* om, const float* ov, int32_t rc, float rm, float rv) {
     if (!a || !om || !ov) return afail(REXSIM_ERR_INVALID, "null argument");
     const int O = a->D.cfg.obs_dim;
