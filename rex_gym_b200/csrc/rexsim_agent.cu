@@ -13,7 +13,6 @@
 namespace rexsim {
 void set_error(const char* msg);   // rexsim_capi.cu (message returned by rexsim_last_error)
 
-constexpr int AG_TM = 64;          // environments per tile
 constexpr int AG_MAX_O = 32, AG_MAX_A = 8, AG_MAX_H1 = 256, AG_MAX_H2 = 128;
 constexpr int RED_BLOCKS = 256;    // partial blocks of the filter update
 
@@ -54,20 +53,24 @@ struct PerformArgs {
     float* action; float* mean; float* logprob; float* value; float* observ_copy;
 };
 
-// Persistent CTAs; for net in {policy, value}: weights -> shared memory once (TMA), then for every tile of AG_TM envs:
-//   normalise -> layer 1 (O x H1) -> layer 2 (H1 x H2, 4 envs x 4 outputs per thread) -> head (H2 x A | 1) + sampling.
-// blockDim.x = (AG_TM / 4) * (H2 / 4).
+// Persistent CTAs, blockIdx.y = network (0 policy, 1 value): weights -> shared memory once (TMA bulk copy), then for every
+// tile of TM envs:  normalise -> layer 1 (O x H1) -> layer 2 (H1 x H2: TM/16 envs x 4 outputs per thread, register tile) ->
+// head (H2 x A | 1) from the register tile + a shared-memory reduction over the H2/4 column groups -> tanh / sampling.
+// blockDim.x = 16 * (H2 / 4)  (400 threads for the reference's 200-100 networks).
+template <int TM>
 __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
+    constexpr int RE = TM / 16;                           // envs per thread in the layer-2 register tile
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
     const RexAgentConfig& c = P.D.cfg;
     const int O = c.obs_dim, A = c.action_dim, H1 = c.hidden1, H2 = c.hidden2;
     const int nt = blockDim.x, tid = threadIdx.x;
+    const int net = blockIdx.y;
     const int wmax = max(P.D.pol_floats, P.D.val_floats);
-    float* W = smem;                          // weights of the current network
+    float* W = smem;                          // weights of this CTA's network
     float* xs = W + wmax;                     // [O][TM] normalised observations
-    float* h1 = xs + AG_MAX_O * AG_TM;        // [H1][TM], reused as [H2][TM] after layer 2
-    float* nrm = h1 + (size_t)H1 * AG_TM;     // [2][O] mean, 1/(std + 1e-8)
+    float* h1 = xs + AG_MAX_O * TM;           // [H1][TM]; reused for the head partials [H2/4][TM][AO]
+    float* nrm = h1 + (size_t)H1 * TM;        // [2][O] mean, 1/(std + 1e-8)
     if (tid == 0) {
         uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
@@ -81,99 +84,111 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
         nrm[tid] = m; nrm[O + tid] = inv;
     }
     __syncthreads();
-    const int ntiles = (P.n + AG_TM - 1) / AG_TM;
+    const int ntiles = (P.n + TM - 1) / TM;
     const uint32_t step = P.step + (uint32_t)P.D.cnt[2];
-    const int eg = tid % (AG_TM / 4), og = tid / (AG_TM / 4);
-    const bool l2_active = og < H2 / 4;               // the launch rounds the block up to AG_TM threads for tiny networks
-    for (int net = 0; net < 2; net++) {
-        const int AO = net == 0 ? A : 1;
-        const int wfloats = net == 0 ? P.D.pol_floats : P.D.val_floats;
-        __syncthreads();                                   // everyone is done with the previous network's weights
-        tma_bulk_load(W, P.D.params + (net == 0 ? 0 : P.D.pol_floats), (uint32_t)wfloats * 4u, &bar, (uint32_t)net);
-        const float* W1 = W; const float* b1 = W1 + O * H1;
-        const float* W2 = b1 + H1; const float* b2 = W2 + H1 * H2;
-        const float* W3 = b2 + H2; const float* b3 = W3 + H2 * AO;
-        const float* logstd = b3 + AO;                      // policy block only
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int e0 = tile * AG_TM;
-            __syncthreads();                                // previous tile's head is done with h1
-            for (int i = tid; i < AG_TM * O; i += nt) {     // coalesced read of the [TM][O] block
-                const int e = i / O, o = i - e * O;
-                float v = 0.f;
-                if (e0 + e < P.n) {
-                    v = P.observ[(size_t)(e0 + e) * O + o];
-                    if (net == 0 && P.observ_copy) P.observ_copy[(size_t)(e0 + e) * O + o] = v;
-                }
-                v = (v - nrm[o]) * nrm[O + o];
-                v = fminf(fmaxf(v, -c.observ_clip), c.observ_clip);
-                xs[o * AG_TM + e] = v;
+    const int eg = tid & 15, og = tid >> 4;
+    const int ngroups = H2 / 4;
+    const bool l2_active = og < ngroups;              // the launch rounds the block up to TM threads for tiny networks
+    const int AO = net == 0 ? A : 1;
+    const int wfloats = net == 0 ? P.D.pol_floats : P.D.val_floats;
+    tma_bulk_load(W, P.D.params + (net == 0 ? 0 : P.D.pol_floats), (uint32_t)wfloats * 4u, &bar, 0u);
+    const float* W1 = W; const float* b1 = W1 + O * H1;
+    const float* W2 = b1 + H1; const float* b2 = W2 + H1 * H2;
+    const float* W3 = b2 + H2; const float* b3 = W3 + H2 * AO;
+    const float* logstd = b3 + AO;                      // policy block only
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int e0 = tile * TM;
+        __syncthreads();                                // previous tile's head is done with h1
+        for (int i = tid; i < TM * O; i += nt) {        // coalesced read of the [TM][O] block
+            const int e = i / O, o = i - e * O;
+            float v = 0.f;
+            if (e0 + e < P.n) {
+                v = P.observ[(size_t)(e0 + e) * O + o];
+                if (net == 0 && P.observ_copy) P.observ_copy[(size_t)(e0 + e) * O + o] = v;
             }
-            __syncthreads();
-            for (int i = tid; i < H1 * AG_TM; i += nt) {    // layer 1
-                const int k = i / AG_TM, e = i - k * AG_TM;
-                float s = b1[k];
-                for (int o = 0; o < O; o++) s = fmaf(xs[o * AG_TM + e], W1[o * H1 + k], s);
-                h1[i] = fmaxf(s, 0.f);
-            }
-            __syncthreads();
-            float acc[4][4];                                // layer 2: 4 envs x 4 outputs per thread
-            if (l2_active) {
-                const float4 bb = ld4(b2 + 4 * og);
+            v = (v - nrm[o]) * nrm[O + o];
+            v = fminf(fmaxf(v, -c.observ_clip), c.observ_clip);
+            xs[o * TM + e] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < H1 * TM; i += nt) {       // layer 1
+            const int k = i / TM, e = i - k * TM;
+            float s = b1[k];
+            for (int o = 0; o < O; o++) s = fmaf(xs[o * TM + e], W1[o * H1 + k], s);
+            h1[i] = fmaxf(s, 0.f);
+        }
+        __syncthreads();
+        float acc[RE][4];                               // layer 2 register tile
+        if (l2_active) {
+            const float4 bb = ld4(b2 + 4 * og);
 #pragma unroll
-                for (int i = 0; i < 4; i++) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
-            }
-            const float* hp = h1 + 4 * eg;
+            for (int i = 0; i < RE; i++) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+            const float* hp = h1 + RE * eg;
             const float* wp = W2 + 4 * og;
 #pragma unroll 4
-            for (int k = 0; k < (l2_active ? H1 : 0); k++) {
-                const float4 h = ld4(hp + k * AG_TM);
-                const float4 w = ld4(wp + k * H2);
-                acc[0][0] = fmaf(h.x, w.x, acc[0][0]); acc[0][1] = fmaf(h.x, w.y, acc[0][1]); acc[0][2] = fmaf(h.x, w.z, acc[0][2]); acc[0][3] = fmaf(h.x, w.w, acc[0][3]);
-                acc[1][0] = fmaf(h.y, w.x, acc[1][0]); acc[1][1] = fmaf(h.y, w.y, acc[1][1]); acc[1][2] = fmaf(h.y, w.z, acc[1][2]); acc[1][3] = fmaf(h.y, w.w, acc[1][3]);
-                acc[2][0] = fmaf(h.z, w.x, acc[2][0]); acc[2][1] = fmaf(h.z, w.y, acc[2][1]); acc[2][2] = fmaf(h.z, w.z, acc[2][2]); acc[2][3] = fmaf(h.z, w.w, acc[2][3]);
-                acc[3][0] = fmaf(h.w, w.x, acc[3][0]); acc[3][1] = fmaf(h.w, w.y, acc[3][1]); acc[3][2] = fmaf(h.w, w.z, acc[3][2]); acc[3][3] = fmaf(h.w, w.w, acc[3][3]);
-            }
-            __syncthreads();                                // all reads of h1 done: reuse it for h2 [H2][TM]
+            for (int k = 0; k < H1; k++) {
+                const float4 w = ld4(wp);
+                float h[RE];
 #pragma unroll
-            for (int j = 0; j < (l2_active ? 4 : 0); j++) {
-                float4 v = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
-                *reinterpret_cast<float4*>(h1 + (4 * og + j) * AG_TM + 4 * eg) = v;
-            }
-            __syncthreads();
-            if (tid < AG_TM && e0 + tid < P.n) {            // head: one thread per env
-                const int e = tid, env = e0 + e;
-                float s[AG_MAX_A];
+                for (int i = 0; i < RE; i += 4) { const float4 t = ld4(hp + i); h[i] = t.x; h[i + 1] = t.y; h[i + 2] = t.z; h[i + 3] = t.w; }
 #pragma unroll
-                for (int a = 0; a < AG_MAX_A; a++) s[a] = a < AO ? b3[a] : 0.f;
-                for (int k = 0; k < H2; k++) {
-                    const float h = h1[k * AG_TM + e];
-#pragma unroll
-                    for (int a = 0; a < AG_MAX_A; a++) if (a < AO) s[a] = fmaf(h, W3[k * AO + a], s[a]);
+                for (int i = 0; i < RE; i++) {
+                    acc[i][0] = fmaf(h[i], w.x, acc[i][0]); acc[i][1] = fmaf(h[i], w.y, acc[i][1]);
+                    acc[i][2] = fmaf(h[i], w.z, acc[i][2]); acc[i][3] = fmaf(h[i], w.w, acc[i][3]);
                 }
-                if (net == 1) {
-                    if (P.value) P.value[env] = s[0];
-                } else {
-                    float lp = 0.f;
+                hp += TM; wp += H2;
+            }
+        }
+        __syncthreads();                                // all reads of h1 done: reuse it for the head partials
+        if (l2_active) {                                // head, part 1: this thread's 4 hidden units x its RE envs
+            float w3[4][AG_MAX_A];
 #pragma unroll
-                    for (int a = 0; a < AG_MAX_A; a++) {
-                        if (a < A) {
-                            const float mu = tanhf(s[a]);
-                            const float ls = logstd[a];
-                            float act = mu, z = 0.f;
-                            if (P.training) {               // network.policy.sample (algorithm.py:116)
-                                const uint32_t genv = P.env_offset + (uint32_t)env;
-                                const float u1 = ((float)(rand_u32(P.seed, genv, step, 2 * a) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                                const float u2 = ((float)(rand_u32(P.seed, genv, step, 2 * a + 1) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                                z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
-                                act = fmaf(expf(ls), z, mu);
-                            }
-                            lp += -0.5f * z * z - ls - 0.9189385332046727f;     // diag-normal log-density
-                            if (P.action) P.action[(size_t)env * A + a] = act;
-                            if (P.mean) P.mean[(size_t)env * A + a] = mu;
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int a = 0; a < AG_MAX_A; a++) w3[j][a] = a < AO ? W3[(4 * og + j) * AO + a] : 0.f;
+#pragma unroll
+            for (int i = 0; i < RE; i++) {
+                const float r0 = fmaxf(acc[i][0], 0.f), r1 = fmaxf(acc[i][1], 0.f), r2 = fmaxf(acc[i][2], 0.f), r3 = fmaxf(acc[i][3], 0.f);
+                float* dst = h1 + ((size_t)og * TM + RE * eg + i) * AO;
+#pragma unroll
+                for (int a = 0; a < AG_MAX_A; a++)
+                    if (a < AO) dst[a] = fmaf(r0, w3[0][a], fmaf(r1, w3[1][a], fmaf(r2, w3[2][a], r3 * w3[3][a])));
+            }
+        }
+        __syncthreads();
+        if (tid < TM && e0 + tid < P.n) {               // head, part 2: one thread per env sums the column groups in order
+            const int e = tid, env = e0 + e;
+            float s[AG_MAX_A];
+#pragma unroll
+            for (int a = 0; a < AG_MAX_A; a++) s[a] = a < AO ? b3[a] : 0.f;
+            for (int g = 0; g < ngroups; g++) {
+                const float* src = h1 + ((size_t)g * TM + e) * AO;
+#pragma unroll
+                for (int a = 0; a < AG_MAX_A; a++) if (a < AO) s[a] += src[a];
+            }
+            if (net == 1) {
+                if (P.value) P.value[env] = s[0];
+            } else {
+                float lp = 0.f;
+#pragma unroll
+                for (int a = 0; a < AG_MAX_A; a++) {
+                    if (a < A) {
+                        const float mu = tanhf(s[a]);
+                        const float ls = logstd[a];
+                        float act = mu, z = 0.f;
+                        if (P.training) {               // network.policy.sample (algorithm.py:116)
+                            const uint32_t genv = P.env_offset + (uint32_t)env;
+                            const float u1 = ((float)(rand_u32(P.seed, genv, step, 2 * a) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                            const float u2 = ((float)(rand_u32(P.seed, genv, step, 2 * a + 1) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                            z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+                            act = fmaf(expf(ls), z, mu);
                         }
+                        lp += -0.5f * z * z - ls - 0.9189385332046727f;     // diag-normal log-density
+                        if (P.action) P.action[(size_t)env * A + a] = act;
+                        if (P.mean) P.mean[(size_t)env * A + a] = mu;
                     }
-                    if (P.logprob) P.logprob[env] = lp;
                 }
+                if (P.logprob) P.logprob[env] = lp;
             }
         }
     }
@@ -254,6 +269,11 @@ __global__ void transform_reward_kernel(const AgentDev D, const float* __restric
 // ---- scans ---------------------------------------------------------------------------------------------------------
 // one thread per episode row, walking backwards in time; rows are laid out by (stride_e, stride_t) so a time-major
 // buffer (stride_e = 1) is read fully coalesced
+// The recurrences are serial in time but every load is independent of them: each thread fetches SCAN_U time steps into
+// registers first (SCAN_U x 2-3 loads in flight per thread), then runs the dependent chain -- without this the kernel waits
+// one DRAM latency per time step.
+constexpr int SCAN_U = 8;
+
 template <bool ADV>
 __global__ void __launch_bounds__(256) row_scan_kernel(const float* __restrict__ reward, const float* __restrict__ value,
                                                        const int32_t* __restrict__ length, int episodes, int L,
@@ -262,19 +282,25 @@ __global__ void __launch_bounds__(256) row_scan_kernel(const float* __restrict__
     if (e >= episodes) return;
     const int len = length[e];
     float agg = 0.f, next_v = 0.f;                           // value[:, 1:] padded with zeros (utility.py:116)
-    for (int t = L - 1; t >= 0; t--) {
-        const int64_t idx = (int64_t)e * se + (int64_t)t * st;
-        const float r = reward[idx];
-        float cur;
-        if (ADV) {
-            const float v = value[idx];
-            cur = (t < len) ? r + discount * next_v - v : 0.f;          // mask * delta
-            next_v = v;
-        } else {
-            cur = (t < len) ? r : 0.f;                                  // mask * reward
+    const int64_t base = (int64_t)e * se;
+    for (int t1 = L; t1 > 0; t1 -= SCAN_U) {
+        float r[SCAN_U], v[SCAN_U];
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int t = t1 - 1 - u;
+            r[u] = t >= 0 ? reward[base + (int64_t)t * st] : 0.f;
+            v[u] = (ADV && t >= 0) ? value[base + (int64_t)t * st] : 0.f;
         }
-        agg = cur + discount * agg;
-        out[idx] = agg;
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int t = t1 - 1 - u;
+            if (t < 0) break;
+            float cur;
+            if (ADV) { cur = (t < len) ? r[u] + discount * next_v - v[u] : 0.f; next_v = v[u]; }   // mask * delta
+            else cur = (t < len) ? r[u] : 0.f;                                                     // mask * reward
+            agg = cur + discount * agg;
+            out[base + (int64_t)t * st] = agg;
+        }
     }
 }
 
@@ -284,16 +310,27 @@ __global__ void __launch_bounds__(256) gae_segments_kernel(const float* __restri
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float next_v = value[(size_t)T * n + e], ret = next_v, adv = 0.f;
-    for (int t = T - 1; t >= 0; t--) {
-        const size_t idx = (size_t)t * n + e;
-        const float r = reward[idx], v = value[idx];
-        const float nd = done[idx] ? 0.f : 1.f;
-        const float delta = r + discount * next_v * nd - v;
-        adv = delta + discount * lambda * nd * adv;
-        ret = r + discount * nd * ret;
-        if (out_adv) out_adv[idx] = adv;
-        if (out_ret) out_ret[idx] = ret;
-        next_v = v;
+    for (int t1 = T; t1 > 0; t1 -= SCAN_U) {
+        float r[SCAN_U], v[SCAN_U]; uint8_t d[SCAN_U];
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int t = t1 - 1 - u;
+            const size_t idx = (size_t)(t >= 0 ? t : 0) * n + e;
+            r[u] = reward[idx]; v[u] = value[idx]; d[u] = done[idx];
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int t = t1 - 1 - u;
+            if (t < 0) break;
+            const size_t idx = (size_t)t * n + e;
+            const float nd = d[u] ? 0.f : 1.f;
+            const float delta = r[u] + discount * next_v * nd - v[u];
+            adv = delta + discount * lambda * nd * adv;
+            ret = r[u] + discount * nd * ret;
+            if (out_adv) out_adv[idx] = adv;
+            if (out_ret) out_ret[idx] = ret;
+            next_v = v[u];
+        }
     }
 }
 
@@ -337,16 +374,17 @@ int64_t rexagent_value_floats(const RexAgentConfig* c) {
     return pad4(O * H1 + H1 + H1 * H2 + H2 + H2 + 1);
 }
 
-static size_t perform_smem_bytes(const RexAgentConfig* c) {
+static size_t perform_smem_bytes(const RexAgentConfig* c, int tm) {
     const size_t wmax = (size_t)(rexagent_policy_floats(c) > rexagent_value_floats(c) ? rexagent_policy_floats(c) : rexagent_value_floats(c));
-    return (wmax + (size_t)AG_MAX_O * AG_TM + (size_t)c->hidden1 * AG_TM + 2 * AG_MAX_O) * sizeof(float);
+    return (wmax + (size_t)AG_MAX_O * tm + (size_t)c->hidden1 * tm + 2 * AG_MAX_O) * sizeof(float);
 }
 
 int rexagent_create(const RexAgentConfig* cfg, RexAgent** out) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!out) return afail(REXSIM_ERR_INVALID, "null argument");
-    if (perform_smem_bytes(cfg) > 227 * 1024) return afail(REXSIM_ERR_UNSUPPORTED, "agent: network does not fit the 227 KB of shared memory");
+    if (perform_smem_bytes(cfg, 128) > 227 * 1024) return afail(REXSIM_ERR_UNSUPPORTED, "agent: network does not fit the 227 KB of shared memory");
+    if (cfg->action_dim * (cfg->hidden2 / 4) > cfg->hidden1) return afail(REXSIM_ERR_UNSUPPORTED, "agent: action_dim * hidden2 / 4 must not exceed hidden1");
     RexAgent* a = new RexAgent();
     a->D.cfg = *cfg;
     a->D.pol_floats = (int)rexagent_policy_floats(cfg); a->D.val_floats = (int)rexagent_value_floats(cfg);
@@ -362,7 +400,8 @@ int rexagent_create(const RexAgentConfig* cfg, RexAgent** out) {
     ACK(cudaMalloc(&a->d_cnt, 4 * sizeof(int32_t)));
     ACK(cudaMemset(a->d_cnt, 0, 4 * sizeof(int32_t)));
     ACK(cudaMalloc(&a->d_partial, (size_t)RED_BLOCKS * 2 * (O + 1) * sizeof(float)));
-    ACK(cudaFuncSetAttribute(perform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_smem_bytes(cfg)));
+    ACK(cudaFuncSetAttribute(perform_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_smem_bytes(cfg, 64)));
+    ACK(cudaFuncSetAttribute(perform_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_smem_bytes(cfg, 128)));
     a->D.params = a->d_params; a->D.filt = a->d_filt; a->D.cnt = a->d_cnt; a->D.partial = a->d_partial;
     ACK(cudaDeviceSynchronize());
     *out = a;
@@ -428,10 +467,17 @@ int rexagent_perform(RexAgent* a, const float* observ, int32_t n, int32_t traini
     PerformArgs P;
     P.D = a->D; P.observ = observ; P.n = n; P.training = training; P.seed = seed; P.step = step; P.env_offset = env_offset;
     P.action = action; P.mean = mean; P.logprob = logprob; P.value = value; P.observ_copy = observ_copy;
-    const int ntiles = (n + AG_TM - 1) / AG_TM;
-    const int blocks = ntiles < a->sm_count ? ntiles : a->sm_count;
-    const int threads = (AG_TM / 4) * (a->D.cfg.hidden2 / 4);
-    perform_kernel<<<blocks, threads < AG_TM ? AG_TM : threads, perform_smem_bytes(&a->D.cfg), (cudaStream_t)stream>>>(P);
+    // one CTA per SM (the weights fill most of the shared memory); the two networks run in different CTAs (blockIdx.y).
+    // Small batches use 64-env tiles so that more SMs get a tile, large ones 128-env tiles (8 x 4 register tile per thread).
+    const int half = a->sm_count / 2 > 0 ? a->sm_count / 2 : 1;
+    const bool big = (n + 127) / 128 >= half;
+    const int tm = big ? 128 : 64;
+    const int ntiles = (n + tm - 1) / tm;
+    dim3 grid(ntiles < half ? ntiles : half, 2);
+    int threads = 16 * (a->D.cfg.hidden2 / 4);
+    if (threads < tm) threads = tm;
+    if (big) perform_kernel<128><<<grid, threads, perform_smem_bytes(&a->D.cfg, 128), (cudaStream_t)stream>>>(P);
+    else perform_kernel<64><<<grid, threads, perform_smem_bytes(&a->D.cfg, 64), (cudaStream_t)stream>>>(P);
     ACK(cudaGetLastError());
     a->launches++;
     return REXSIM_OK;

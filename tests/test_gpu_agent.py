@@ -118,7 +118,7 @@ def test_rollout_graph_equals_the_step_by_step_loop():
     import rex_gym_b200 as R
     from rex_gym_b200.agents import ForwardGaussianPolicy, Rollout
     n, T = 512, 16
-    kw = dict(task="walk", num_envs=n, signal_type="ik", normalize=True, auto_reset=True, max_episode_steps=40, target_position=2.0, backwards=False)
+    kw = dict(task="walk", num_envs=n, signal_type="ik", normalize=True, auto_reset=True, max_episode_steps=25, target_position=2.0, backwards=False)
     outs = []
     for use_graph in (False, True):
         env = R.BatchedRexEnv(**kw)
@@ -148,7 +148,7 @@ def test_rollout_graph_equals_the_step_by_step_loop():
         np.testing.assert_array_equal(b0[k].cpu().numpy(), b1[k].cpu().numpy(), err_msg=k)
     assert f0["observ_count"] == f1["observ_count"] == 2 * T * n
     np.testing.assert_array_equal(f0["observ_var_sum"], f1["observ_var_sum"])
-    assert b0["done"].any()                                              # LimitDuration(40) fired inside the second window
+    assert b0["done"].any()                                              # LimitDuration(25) fired inside the second window
     assert np.abs((a0["action"] - a0["mean"]).cpu().numpy()).max() > 1e-3   # training: sampled actions
 
 
