@@ -123,14 +123,16 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
             const float4 bb = ld4(b2 + 4 * og);
 #pragma unroll
             for (int i = 0; i < RE; i++) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
-            const float* hp = h1 + RE * eg;
+            // thread's envs: chunk c (of RE/4) covers envs 64*c + 4*eg .. +3, so the 16 lanes of a half-warp read 256
+            // contiguous bytes per LDS.128 (bank-conflict free; envs 8*eg .. 8*eg+7 would be a 4-way conflict)
+            const float* hp = h1 + 4 * eg;
             const float* wp = W2 + 4 * og;
 #pragma unroll 4
             for (int k = 0; k < H1; k++) {
                 const float4 w = ld4(wp);
                 float h[RE];
 #pragma unroll
-                for (int i = 0; i < RE; i += 4) { const float4 t = ld4(hp + i); h[i] = t.x; h[i + 1] = t.y; h[i + 2] = t.z; h[i + 3] = t.w; }
+                for (int i = 0; i < RE; i += 4) { const float4 t = ld4(hp + (i / 4) * 64); h[i] = t.x; h[i + 1] = t.y; h[i + 2] = t.z; h[i + 3] = t.w; }
 #pragma unroll
                 for (int i = 0; i < RE; i++) {
                     acc[i][0] = fmaf(h[i], w.x, acc[i][0]); acc[i][1] = fmaf(h[i], w.y, acc[i][1]);
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
 #pragma unroll
             for (int i = 0; i < RE; i++) {
                 const float r0 = fmaxf(acc[i][0], 0.f), r1 = fmaxf(acc[i][1], 0.f), r2 = fmaxf(acc[i][2], 0.f), r3 = fmaxf(acc[i][3], 0.f);
-                float* dst = h1 + ((size_t)og * TM + RE * eg + i) * AO;
+                float* dst = h1 + ((size_t)og * TM + (i / 4) * 64 + 4 * eg + (i & 3)) * AO;
 #pragma unroll
                 for (int a = 0; a < AG_MAX_A; a++)
                     if (a < AO) dst[a] = fmaf(r0, w3[0][a], fmaf(r1, w3[1][a], fmaf(r2, w3[2][a], r3 * w3[3][a])));
