@@ -235,6 +235,31 @@ def main():
         extra = {"envs_per_gpu": nb, "steps": Kb, "ms_per_step": float(tb.item()) / Kb,
                  "value": world * nb * Kb / (float(tb.item()) * 1e-3), "unit": "env-steps/s", "error_flags_or": envb.check_errors()}
         envb.close()
+    # ---- the all-device rollout (policy inference + env step + filter update per control step,
+    #      one CUDA graph per 32-step window), same workload, reported as an extra ----------------------------------------
+    rollout = None
+    try:
+        from rex_gym_b200.agents import ForwardGaussianPolicy, Rollout
+        envr = R.BatchedRexEnv(num_envs=n, device=f"cuda:{local}", seed=1234, env_offset=rank * n, **WORKLOAD)
+        net = ForwardGaussianPolicy(envr.obs_dim, envr.action_dim, device=f"cuda:{local}")
+        ro = Rollout(envr, net, 32, seed=1234, training=True, use_graph=True)
+        for _ in range(3):
+            ro.collect()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            ro.collect()
+        b.record(); barrier()
+        tr = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        rollout = {"what": "ForwardGaussianPolicy(200-100) perform + env step + filter update per control step, CUDA graph of 32 steps",
+                   "ms_per_control_step": float(tr.item()) / 320, "value": world * n * 320 / (float(tr.item()) * 1e-3), "unit": "env-steps/s",
+                   "kernels_per_control_step": 3}
+        envr.close(); net.close()
+    except Exception as e:  # the extra must never take the headline down with it
+        rollout = {"error": str(e)}
     if rank == 0:
         peaks = {}
         try:
@@ -251,14 +276,18 @@ def main():
             "config": {"workload": f"{n} envs/GPU walk-ik flat terrain, fused ABA+IK+motor kernel (BASELINE configs[1])",
                        "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "wrappers": "ClipAction+RangeNormalize+LimitDuration(2000)+auto-reset fused", "l2": "flushed between timed steps (256 MiB memset)",
-                       "obs_allgather_us": ag_us, "error_flags_or": err, "north_star_size": extra},
+                       "obs_allgather_us": ag_us, "error_flags_or": err, "north_star_size": extra, "rollout_with_policy": rollout},
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * A * 4,
                     "d2h_bytes_per_step": n * (O * 4 + 4 + 1) + 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "of": "measured" if peaks else "fallback",
-                         "note": "state fits L2 and the kernel is fp32-issue/latency bound, see DESIGN.md"},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch at this workload size, from the
+                         # ncu --set full capture summarised in profiles/r01b_step_kernel_4096_ncu_raw.txt (the 1 MB state stays in
+                         # the 126 MB L2 across launches: reads are first touches of the flushed lines, writes never reach DRAM)
+                         "traffic": 987648 if n == 4096 else None, "of": "measured" if peaks else "fallback",
+                         "note": "state fits L2; the kernel is issue/latency bound (one partial wave: 0.43 waves/SM, issue slots 24 % busy, "
+                                 "14.7 M warp instructions per launch), see DESIGN.md section 5 and profiles/"},
         }
         try:
             line["cpu_baseline"] = cpu_baseline_leg()
