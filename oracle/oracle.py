@@ -47,7 +47,7 @@ class RexoConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("seed", C.c_uint64),
         ("nfields", C.c_int32), ("fields", C.POINTER(C.c_float)), ("friction", C.c_double),
         ("residual_threshold", C.c_double), ("erp_contact", C.c_double), ("erp_joint", C.c_double),
-        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("pose_values", C.c_double * 5),
+        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("gait_clock_scale", C.c_double), ("pose_values", C.c_double * 5),
     ]
 
 
@@ -198,7 +198,8 @@ class OracleSim:
                  target_orient=None, init_orient=None, energy_weight=None, normalize=False,
                  max_episode_steps=0, seed=1234, nfields=0, fields=None, toes_only=False, settle=True,
                  solver_iterations=None, residual_threshold=1e-7, env_offset=0,
-                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, terrain_full_toe=False):
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, terrain_full_toe=False,
+                 gait_clock_scale=1.0):
         self.L = lib(f32)
         self.model, self.model_json = load_model(mark, toes_only=toes_only, terrain_full_toe=terrain_full_toe)
         c = RexoConfig()
@@ -233,6 +234,7 @@ class OracleSim:
         c.erp_contact, c.erp_joint = 0.08, 0.2
         c.settle_on_reset = int(settle)
         c.env_offset = int(env_offset)
+        c.gait_clock_scale = float(gait_clock_scale)
         for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):
             c.pose_values[k] = float("nan") if v is None else float(v)
         self.cfg = c

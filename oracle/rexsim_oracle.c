@@ -725,7 +725,7 @@ static void walk_command(RexoSim* s, RexoEnv* e, const double* action, double* c
             if (brakes == 0.0) e->stay_still = 1;
         }
         double direction = step_length < 0 ? -1.0 : 1.0;
-        ik_signal_common(e, 0, t, pos, rpy, step_length, 0.0, 0.0, period, direction, cmd);
+        ik_signal_common(e, 0, t * s->c.gait_clock_scale, pos, rpy, step_length, 0.0, 0.0, period, direction, cmd);
     } else {                               /* _open_loop_signal :292-315 */
         double period = 1.0 / 8, l_a = 0.1, f_a = l_a * 2;
         if (e->goal_reached) {
@@ -767,7 +767,7 @@ static void gallop_command(RexoSim* s, RexoEnv* e, double* action, double* cmd) 
             double brakes = (e->end_time <= t && t <= pb + e->end_time) ? 1 - (t - e->end_time) : 0.0;   /* :232-239 */
             step_length *= brakes;
         }
-        ik_signal_common(e, 1, t, pos, rpy, step_length, 0.0, 0.0, 0.3, 1.0, cmd);
+        ik_signal_common(e, 1, t * s->c.gait_clock_scale, pos, rpy, step_length, 0.0, 0.0, 0.3, 1.0, cmd);
     } else {                               /* :287-304 */
         if (e->goal_reached) {
             double pb = 1. + .0;
@@ -810,7 +810,7 @@ static void turn_command(RexoSim* s, RexoEnv* e, const double* action, double* c
         double step_rotation = dirv + action[0];
         double step_period = 0.75 + action[1];
         if (e->goal_reached) e->stay_still = 1;
-        ik_signal_common(e, 0, t, pos, rpy, 0.02, 0.0, step_rotation, step_period, 1.0, cmd);
+        ik_signal_common(e, 0, t * s->c.gait_clock_scale, pos, rpy, 0.02, 0.0, step_rotation, step_period, 1.0, cmd);
     } else {                               /* :271-311 */
         if (e->goal_reached) e->stay_still = 1;
         const double period = 1.0 / 10.0;  /* STEP_PERIOD turn_env.py:17 */

@@ -22,7 +22,7 @@ class RexSimConfig(C.Structure):
         ("seed", C.c_uint64), ("nfields", C.c_int32), ("fields", C.c_void_p),
         ("friction", C.c_float), ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
         ("toe_npts", C.c_int32), ("toe_margin", C.c_float), ("env_offset", C.c_int32),
-        ("pose_values", C.c_float * 5),
+        ("gait_clock_scale", C.c_double), ("pose_values", C.c_float * 5),
     ]
 
 

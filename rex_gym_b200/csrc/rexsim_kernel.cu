@@ -909,14 +909,15 @@ struct GaitState { double phi; int last_step; float alpha; };
 
 // GaitPlanner.loop + Kinematics.solve for the own leg; il = IK leg index (FR,FL,RR,RL) = lane ^ 1
 template <bool ROT>
-__device__ __forceinline__ void ik_signal(GaitState& G, bool gallop, int step_counter, double dtd, int leg,
+__device__ __forceinline__ void ik_signal(GaitState& G, bool gallop, int step_counter, double dtd, double clk, int leg,
                                           float base_x, float base_z, float v, float w_rot, double T, float direction, float* cmd) {
     const int il = leg ^ 1;
     // fp64 timing must round exactly like the reference's Python floats: no FMA contraction (a - b*c is NOT fused)
-    double now = __dmul_rn((double)step_counter, dtd);
+    // clk = gait_clock_scale: (step * dt) * clk in exactly the oracle's operation order; x * 1.0 is exact
+    double now = __dmul_rn(__dmul_rn((double)step_counter, dtd), clk);
     if (T <= 0.01) T = 0.01;
     if (G.phi >= 0.99) G.last_step = step_counter;
-    G.phi = __ddiv_rn(__dsub_rn(now, __dmul_rn((double)G.last_step, dtd)), T);
+    G.phi = __ddiv_rn(__dsub_rn(now, __dmul_rn(__dmul_rn((double)G.last_step, dtd), clk)), T);
     double off = gallop ? ((il >= 2) ? 0.8 : 0.0) : ((il == 1 || il == 2) ? 0.5 : 0.0);
     double ph = __dadd_rn(G.phi, off);
     if (ph >= 1) ph = __dsub_rn(ph, 1.);
@@ -997,7 +998,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
                 if (brakes == 0.0) K.flags |= FL_STILL;
             }
             float direction = sl < 0 ? -1.f : 1.f;
-            ik_signal<false>(K.G, false, K.step_counter, dtd, leg, base_x, 0.f, (float)sl, 0.f, period, direction, cmd);
+            ik_signal<false>(K.G, false, K.step_counter, dtd, P.cfg.gait_clock_scale, leg, base_x, 0.f, (float)sl, 0.f, period, direction, cmd);
         } else {
             double l_a = 0.1, f_a = 0.2;
             if (K.flags & FL_GOAL) {
@@ -1032,7 +1033,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
                 double brakes = (end_t <= t && t <= pb + end_t) ? 1 - (t - end_t) : 0.0;
                 sl *= brakes;
             }
-            ik_signal<false>(K.G, true, K.step_counter, dtd, leg, 0.01f, -0.007f, (float)sl, 0.f, 0.3, 1.f, cmd);
+            ik_signal<false>(K.G, true, K.step_counter, dtd, P.cfg.gait_clock_scale, leg, 0.01f, -0.007f, (float)sl, 0.f, 0.3, 1.f, cmd);
         } else {
             float a0 = act[(leg < 2) ? 0 : 2], a1 = act[(leg < 2) ? 1 : 3];
             if (K.flags & FL_GOAL) {
@@ -1064,7 +1065,7 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
             float step_rotation = (float)(dirv + (double)act[0]);
             double step_period = 0.75 + (double)act[1];
             if (K.flags & FL_GOAL) K.flags |= FL_STILL;
-            ik_signal<true>(K.G, false, K.step_counter, dtd, leg, 0.009f, 0.f, 0.02f, step_rotation, step_period, 1.f, cmd);
+            ik_signal<true>(K.G, false, K.step_counter, dtd, P.cfg.gait_clock_scale, leg, 0.009f, 0.f, 0.02f, step_rotation, step_period, 1.f, cmd);
         } else {
             if (K.flags & FL_GOAL) K.flags |= FL_STILL;
             const float extension = 0.1f, swing = 0.03f + act[0], swipe = 0.05f + act[1];

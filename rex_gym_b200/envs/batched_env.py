@@ -78,7 +78,7 @@ class BatchedRexEnv(object):
                  energy_weight=None, signal_type="ik", terrain_type="plane", terrain_id=None, mark="base",
                  normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
                  motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0,
-                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None):
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, gait_clock_scale=1.0):
         if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
             raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
         if task not in TASKS or signal_type not in SIGNALS:
@@ -121,6 +121,7 @@ class BatchedRexEnv(object):
         c.w_distance, c.w_drift, c.w_shake = 1.0, 2.0, 0.005                            # rex_gym_env.py:56-59
         c.w_energy = energy_weight if energy_weight is not None else (0.005 if task == "gallop" else 0.0005)
         c.normalize, c.max_episode_steps, c.auto_reset, c.seed = int(normalize), int(max_episode_steps), int(auto_reset), seed
+        c.gait_clock_scale = float(gait_clock_scale)     # GaitPlanner clock / simulation clock (the reference reads the wall clock)
         for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):      # poses_env.py:49-53 (None = rotate per reset)
             c.pose_values[k] = float("nan") if v is None else float(v)
         self._fields = None

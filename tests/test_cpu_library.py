@@ -46,6 +46,7 @@ def test_create_rejects_bad_arguments_without_touching_the_gpu():
     tb = np.zeros(952, np.float32)
     assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -1          # num_envs = 0
     cfg.num_envs, cfg.num_motors, cfg.task, cfg.action_repeat, cfg.solver_iterations, cfg.sim_dt_d, cfg.toe_npts = 8, 12, 0, 5, 60, 0.001, 27
+    cfg.gait_clock_scale = 1.0
     assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 951, C.byref(h)) == -2          # model table size
     cfg.num_motors, cfg.task = 18, 1
     assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952 + 192, C.byref(h)) == -4    # arm + gallop not built

@@ -78,6 +78,7 @@ CASES = [("walk", "ik", dict(target_position=2.0, backwards=False)),
          ("standup", "ol", dict()),
          ("standup", "ol", dict(mark="arm")),                      # BASELINE config 5 model: 18 DOF, arm limit rows always active
          ("walk", "ik", dict(mark="arm", target_position=2.0, backwards=True)),
+         ("walk", "ik", dict(target_position=2.0, backwards=False, gait_clock_scale=16.0)),   # wall-clock gait emulation
          ("poses", "ik", dict()),                                   # RexPosesEnv: pose rotates per reset, target drawn in range
          ("poses", "ik", dict(base_y=0.0, base_z=0.0, base_roll=0.0, base_pitch=0.4, base_yaw=0.0))]
 

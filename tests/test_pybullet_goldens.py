@@ -120,3 +120,40 @@ def test_fixture_matches_the_reference_checkpoints():
         np.testing.assert_array_equal(G[task + "_ol_observ"], v["memory/Variable_1"][:12, :161])
         np.testing.assert_array_equal(G[task + "_ol_action"], v["memory/Variable_2"][:12, :160])
         np.testing.assert_array_equal(G[task + "_ol_reward"], v["memory/Variable_5"][:12, :160])
+
+
+def test_wall_clock_gait_of_the_recorded_walk_ik_episodes():
+    """GaitPlanner.loop reads time.time() (gait_planner.py:108-110).  The walk-ik episodes stored in the shipped checkpoint
+    show what that meant in training: a 7.8-8.0 control-step ripple in roll/pitch, i.e. a gait cycle of ~8 control steps =
+    40 ms of simulation time instead of the nominal 0.65 s -- the wall clock ran ~16x faster than the simulation.  With
+    gait_clock_scale=16 the restatement reproduces the recorded regime (a level, shuffling walk: roll/pitch ripple of a few
+    mrad for the whole window); with the simulation clock (scale 1) the same actions give the nominal trot, which is a
+    different motion altogether (and tips over in this model)."""
+    ref = denorm(G["walk_ik_observ"])
+    ac = G["walk_ik_action"]
+    np.testing.assert_array_equal(ref[:, 0], 0.0)                       # pristine reset observation
+    for ep in range(3):
+        seg = ref[ep, 100:300, 1] - ref[ep, 100:300, 1].mean()
+        spec = np.abs(np.fft.rfft(seg)); k = int(np.argmax(spec[10:])) + 10   # ignore the slow drift (periods > 20 steps)
+        assert 7.0 < len(seg) / k < 9.0                                 # recorded ripple period in control steps
+        s = OracleSim(1, "walk", "ik", normalize=True, settle=2, target_position=2.0, backwards=False, gait_clock_scale=16.0)
+        s.reset()
+        out = []
+        for t in range(300):
+            o, r, d = s.step(ac[ep, t][None, :])
+            assert not d[0], (ep, t)
+            out.append(denorm(o[0]))
+        out = np.array(out)
+        for j in (0, 1):                                                # roll, pitch ripple: same size as recorded
+            ours, real = out[50:, j].std(), ref[ep, 51:301, j].std()
+            assert 0.4 * real < ours < 2.5 * real, (ep, j, ours, real)
+        assert np.abs(out[:, :2]).max() < 0.04                          # level for the whole window (recorded: < 0.02)
+    s = OracleSim(1, "walk", "ik", normalize=True, settle=2, target_position=2.0, backwards=False)      # simulation clock
+    s.reset()
+    big = 0.0
+    for t in range(200):
+        o, r, d = s.step(ac[0, t][None, :])
+        big = max(big, float(np.abs(denorm(o[0])[:2]).max()))
+        if d[0]:
+            break
+    assert big > 0.1                                                     # the nominal trot rocks the base 25x more

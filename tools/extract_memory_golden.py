@@ -43,6 +43,11 @@ def main():
         out[name + "_observ"] = ob[:EPISODES, :STEPS + 1].astype(np.float32)
         out[name + "_reward"] = rw[:EPISODES, :STEPS].astype(np.float32)
         print(name, os.path.basename(prefix), "memory", ob.shape, "->", out[name + "_observ"].shape)
+    # walk-ik: NOT replayable step by step (the gait phase ran on the wall clock, gait_planner.py:108-110), kept for the
+    # statistical test of the wall-clock emulation (gait_clock_scale): 300 steps of 6 episodes
+    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ik")), ["memory/Variable_1", "memory/Variable_2"])
+    out["walk_ik_action"] = v["memory/Variable_2"][:6, :300].astype(np.float32)
+    out["walk_ik_observ"] = v["memory/Variable_1"][:6, :301].astype(np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
