@@ -70,6 +70,14 @@ int rexagent_perform(RexAgent* a, const float* observ, int32_t n, int32_t traini
                      void* stream);
 /* update both filters with one batch (observ dev [n][O], reward dev [n]); also advances the device step counter */
 int rexagent_experience(RexAgent* a, const float* observ, const float* reward, int32_t n, void* stream);
+/* Environment-sharded rollouts (one rank per GPU): the filters must see the WHOLE batch, so the update splits in two around
+ * the one real exchange step of this path -- a sum all-reduce of 2*(O+1) floats:
+ *   rexagent_experience_partial  -> sums dev [O+1][2] = (sum(x - mean), sum((x - mean)^2)) of this rank's batch, filters untouched
+ *   ncclAllReduce(sums, sum)        (torch.distributed.all_reduce on the same stream)
+ *   rexagent_experience_finalize -> applies the global sums with n_total = envs of all ranks; observ/reward: this rank's batch
+ *                                   (only element 0 is read, for the count <= 1 corner of normalize.py:88) */
+int rexagent_experience_partial(RexAgent* a, const float* observ, const float* reward, int32_t n, float* sums, void* stream);
+int rexagent_experience_finalize(RexAgent* a, const float* sums, int32_t n_total, const float* observ, const float* reward, void* stream);
 /* reward filter transform (scale by the running std, clip): in dev [n] -> out dev [n] */
 int rexagent_transform_reward(RexAgent* a, const float* reward, int32_t n, float* out, void* stream);
 

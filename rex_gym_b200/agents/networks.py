@@ -152,12 +152,24 @@ class ForwardGaussianPolicy(object):
                                                  ptr(observ_copy), self._stream()))
         return out
 
-    def experience(self, observ, reward):
+    def experience(self, observ, reward, group=None):
         """PPOAlgorithm._define_experience's filter updates (algorithm.py:157-161) for one batch; advances the device-side
-        step counter that keys the next perform's noise."""
+        step counter that keys the next perform's noise.  With torch.distributed initialised (env-sharded rollout, one rank per
+        GPU) the batch statistics are summed over the ranks first -- one all-reduce of 2*(O+1) floats, the only exchange
+        step of this path -- so every rank keeps the filter state of the whole batch."""
+        import torch.distributed as dist
         n = observ.shape[0]
+        sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         with torch.cuda.device(self.device):
-            _capi.check(self._L.rexagent_experience(self._h, observ.data_ptr(), reward.data_ptr(), n, self._stream()))
+            if not sharded:
+                _capi.check(self._L.rexagent_experience(self._h, observ.data_ptr(), reward.data_ptr(), n, self._stream()))
+                return
+            if getattr(self, "_sums", None) is None:
+                self._sums = torch.zeros((self.O + 1, 2), dtype=torch.float32, device=self.device)
+            _capi.check(self._L.rexagent_experience_partial(self._h, observ.data_ptr(), reward.data_ptr(), n, self._sums.data_ptr(), self._stream()))
+            dist.all_reduce(self._sums, op=dist.ReduceOp.SUM, group=group)
+            _capi.check(self._L.rexagent_experience_finalize(self._h, self._sums.data_ptr(), n * dist.get_world_size(group),
+                                                              observ.data_ptr(), reward.data_ptr(), self._stream()))
 
     def transform_reward(self, reward, out=None):
         out = torch.empty_like(reward) if out is None else out

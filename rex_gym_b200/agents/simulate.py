@@ -32,6 +32,9 @@ class Rollout(object):
         self.done = torch.zeros((T, N), dtype=torch.uint8, device=dev)
         self._cur = torch.zeros((N, O), **f32)             # observation the next action is computed from
         self._graph = None
+        import torch.distributed as dist
+        if use_graph and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            use_graph = False      # env-sharded: the per-step filter all-reduce runs through c10d; the plain loop is used
         self._use_graph = use_graph
         self.reset()
 

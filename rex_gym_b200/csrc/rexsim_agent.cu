@@ -200,7 +200,21 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
 // per column j: S1 = sum(x - mean), S2 = sum((x - mean)^2) over the batch (block partials, then the last block to
 // finish adds them in a fixed order -> bit-reproducible); count += n; new_mean = mean + S1/count;
 // var_sum += S2 - S1^2/count  ( = sum (x - mean)(x - new_mean) ).
-struct ExperienceArgs { AgentDev D; const float* __restrict__ observ; const float* __restrict__ reward; int n; };
+struct ExperienceArgs { AgentDev D; const float* __restrict__ observ; const float* __restrict__ reward; int n; float* sums_out; };
+
+// finalisation shared by the single-GPU kernel and the sharded path (sums = [O+1][2] (S1, S2) over ALL ranks, n_total likewise)
+__device__ __forceinline__ void filters_finalize(const AgentDev& D, int col, float s1, float s2, int n_total, float first_value) {
+    const int O = D.cfg.obs_dim;
+    const int which = col < O ? 0 : 1;
+    const int cnt = D.cnt[which] + n_total;
+    const float step = (float)cnt;
+    float* meanp = col < O ? &D.filt[col] : &D.filt[2 * O];
+    float* varp = col < O ? &D.filt[O + col] : &D.filt[2 * O + 1];
+    float new_mean = *meanp + s1 / step;
+    if (cnt <= 1) new_mean = first_value;                                   // tf.cond(count > 1, new_mean, value[0])
+    *varp += s2 - s1 * (s1 / step);
+    *meanp = new_mean;
+}
 
 __global__ void __launch_bounds__(256) experience_kernel(const ExperienceArgs P) {
     const int O = P.D.cfg.obs_dim, C = O + 1;
@@ -241,22 +255,23 @@ __global__ void __launch_bounds__(256) experience_kernel(const ExperienceArgs P)
             s1 += __ldcg(&P.D.partial[(size_t)b * 2 * C + 2 * tid]);
             s2 += __ldcg(&P.D.partial[(size_t)b * 2 * C + 2 * tid + 1]);
         }
-        const int which = tid < O ? 0 : 1;
-        const int cnt = P.D.cnt[which] + P.n;
-        const float step = (float)cnt;
-        float* meanp = tid < O ? &P.D.filt[tid] : &P.D.filt[2 * O];
-        float* varp = tid < O ? &P.D.filt[O + tid] : &P.D.filt[2 * O + 1];
-        float new_mean = *meanp + s1 / step;
-        if (cnt <= 1) new_mean = tid < O ? P.observ[tid] : P.reward[0];     // tf.cond(count > 1, new_mean, value[0])
-        *varp += s2 - s1 * (s1 / step);
-        *meanp = new_mean;
+        if (P.sums_out) { P.sums_out[2 * tid] = s1; P.sums_out[2 * tid + 1] = s2; }          // sharded: another rank's sums are added first
+        else filters_finalize(P.D, tid, s1, s2, P.n, tid < O ? P.observ[tid] : P.reward[0]);
     }
     __syncthreads();
     if (tid == 0) {
-        P.D.cnt[0] += P.n; P.D.cnt[1] += P.n;
-        P.D.cnt[2] += 1;          // device step counter: the next perform draws fresh noise
+        if (!P.sums_out) { P.D.cnt[0] += P.n; P.D.cnt[1] += P.n; P.D.cnt[2] += 1; }     // step counter: the next perform draws fresh noise
         P.D.cnt[3] = 0;
     }
+}
+
+// sharded rollouts: sums = this rank's partial sums after an all-reduce(sum) over the ranks; n_total = envs of all ranks
+__global__ void experience_finalize_kernel(const AgentDev D, const float* __restrict__ sums, int n_total,
+                                           const float* __restrict__ observ, const float* __restrict__ reward) {
+    const int O = D.cfg.obs_dim, tid = threadIdx.x;
+    if (tid <= O) filters_finalize(D, tid, sums[2 * tid], sums[2 * tid + 1], n_total, tid < O ? observ[tid] : reward[0]);
+    __syncthreads();
+    if (tid == 0) { D.cnt[0] += n_total; D.cnt[1] += n_total; D.cnt[2] += 1; }
 }
 
 __global__ void transform_reward_kernel(const AgentDev D, const float* __restrict__ r, int n, float* __restrict__ out) {
@@ -487,10 +502,29 @@ int rexagent_perform(RexAgent* a, const float* observ, int32_t n, int32_t traini
 int rexagent_experience(RexAgent* a, const float* observ, const float* reward, int32_t n, void* stream) {
     if (!a || !observ || !reward) return afail(REXSIM_ERR_INVALID, "null argument");
     if (n <= 0) return afail(REXSIM_ERR_INVALID, "agent: n must be positive");
-    ExperienceArgs P; P.D = a->D; P.observ = observ; P.reward = reward; P.n = n;
+    ExperienceArgs P; P.D = a->D; P.observ = observ; P.reward = reward; P.n = n; P.sums_out = nullptr;
     int blocks = (n + 255) / 256;
     if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
     experience_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    ACK(cudaGetLastError());
+    a->launches++;
+    return REXSIM_OK;
+}
+int rexagent_experience_partial(RexAgent* a, const float* observ, const float* reward, int32_t n, float* sums, void* stream) {
+    if (!a || !observ || !reward || !sums) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n <= 0) return afail(REXSIM_ERR_INVALID, "agent: n must be positive");
+    ExperienceArgs P; P.D = a->D; P.observ = observ; P.reward = reward; P.n = n; P.sums_out = sums;
+    int blocks = (n + 255) / 256;
+    if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+    experience_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    ACK(cudaGetLastError());
+    a->launches++;
+    return REXSIM_OK;
+}
+int rexagent_experience_finalize(RexAgent* a, const float* sums, int32_t n_total, const float* observ, const float* reward, void* stream) {
+    if (!a || !sums || !observ || !reward) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (n_total <= 0) return afail(REXSIM_ERR_INVALID, "agent: n_total must be positive");
+    experience_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a->D, sums, n_total, observ, reward);
     ACK(cudaGetLastError());
     a->launches++;
     return REXSIM_OK;

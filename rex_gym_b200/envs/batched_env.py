@@ -156,6 +156,7 @@ class BatchedRexEnv(object):
         self._h_act = torch.zeros((N, A), dtype=torch.float32).pin_memory()
         self._h_out = torch.zeros((nb_out,), dtype=torch.uint8).pin_memory()
         self._h_act_np = self._h_act.numpy()
+        self._h_act_ptr, self._h_out_ptr = self._h_act.data_ptr(), self._h_out.data_ptr()
         ho = self._h_out.numpy()
         self._h_obs = ho[:nb_obs].view(np.float32).reshape(N, O)
         self._h_reward = ho[nb_obs:nb_obs + nb_rew].view(np.float32)
@@ -223,9 +224,14 @@ class BatchedRexEnv(object):
         if not np.isfinite(a).all():
             raise ValueError("Invalid action: non-finite values")
         np.copyto(self._h_act_np, a)
-        with torch.cuda.device(self.device):
-            _capi.check(self._L.rexsim_step_host(self._h, self._h_act.data_ptr(), self._h_out.data_ptr(), self._stream()))
-        if int(self._h_err[0]) & ERR_NONFINITE:
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self.device):
+                rc = self._L.rexsim_step_host(self._h, self._h_act_ptr, self._h_out_ptr, self._stream())
+        else:
+            rc = self._L.rexsim_step_host(self._h, self._h_act_ptr, self._h_out_ptr, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _capi.check(rc)
+        if self._h_err[0] & ERR_NONFINITE:
             raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
         return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), _Info(self)
 
