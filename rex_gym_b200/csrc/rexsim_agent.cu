@@ -403,6 +403,7 @@ int rexagent_create(const RexAgentConfig* cfg, RexAgent** out) {
     if (perform_smem_bytes(cfg, 128) > 227 * 1024) return afail(REXSIM_ERR_UNSUPPORTED, "agent: network does not fit the 227 KB of shared memory");
     if (cfg->action_dim * (cfg->hidden2 / 4) > cfg->hidden1) return afail(REXSIM_ERR_UNSUPPORTED, "agent: action_dim * hidden2 / 4 must not exceed hidden1");
     RexAgent* a = new RexAgent();
+    struct Guard { RexAgent* a; ~Guard() { if (a) rexagent_destroy(a); } } guard{a};  // frees everything on an early return
     a->D.cfg = *cfg;
     a->D.pol_floats = (int)rexagent_policy_floats(cfg); a->D.val_floats = (int)rexagent_value_floats(cfg);
     const size_t np = (size_t)a->D.pol_floats + a->D.val_floats;
@@ -421,6 +422,7 @@ int rexagent_create(const RexAgentConfig* cfg, RexAgent** out) {
     ACK(cudaFuncSetAttribute(perform_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_smem_bytes(cfg, 128)));
     a->D.params = a->d_params; a->D.filt = a->d_filt; a->D.cnt = a->d_cnt; a->D.partial = a->d_partial;
     ACK(cudaDeviceSynchronize());
+    guard.a = nullptr;
     *out = a;
     return REXSIM_OK;
 }

@@ -82,6 +82,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     const int mt_floats = cfg->num_motors == 18 ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS;
     if (n_model_floats != mt_floats) return fail(REXSIM_ERR_MODEL, "model table size mismatch");
     RexSim* s = new RexSim();
+    struct Guard { RexSim* s; ~Guard() { if (s) rexsim_destroy(s); } } guard{s};      // frees everything on an early return
     memset(&s->P, 0, sizeof(Params));
     s->P.cfg = *cfg;
     s->P.cfg.sim_dt = (float)cfg->sim_dt_d;
@@ -135,6 +136,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
         s->launches++;
     }
     CK(cudaDeviceSynchronize());
+    guard.s = nullptr;
     *out = s;
     return REXSIM_OK;
 }
