@@ -368,11 +368,26 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         {
             // toe prism: the deepest hull vertex is the profile vertex minimising z3.x*x + z3.z*z on the y face that
             // minimises z3.y*y (exact support function of the hull: 2 FMA per profile vertex)
-            float bt = 1e30f; int jt = 0;
-#pragma unroll 4
-            for (int j = 0; j < npts; j++) {
+            // The profile is an ordered arc of a convex polygon, so d(j) = z3.x*x_j + z3.z*z_j has at most one interior
+            // minimum along it: sample every 8th vertex (+ the last), then the 7 neighbours either side of the best sample --
+            // 9 + 15 evaluations instead of 68, same argmin as the full scan (ties aside).
+            float bc = 1e30f; int jc = 0;
+#pragma unroll 3
+            for (int j = 0; j < npts; j += 8) {
                 float d = fmaf(z3.x, TPl[2 * j], z3.z * TPl[2 * j + 1]);
-                if (d < bt) { bt = d; jt = j; }
+                if (d < bc) { bc = d; jc = j; }
+            }
+            {
+                const int j = npts - 1;
+                float d = fmaf(z3.x, TPl[2 * j], z3.z * TPl[2 * j + 1]);
+                if (d < bc) { bc = d; jc = j; }
+            }
+            float bt = bc; int jt = jc;
+            const int jlo = max(jc - 7, 0), jhi = min(jc + 7, npts - 1);
+#pragma unroll 3
+            for (int j = jlo; j <= jhi; j++) {
+                float d = fmaf(z3.x, TPl[2 * j], z3.z * TPl[2 * j + 1]);
+                if (d < bt || (d == bt && j < jt)) { bt = d; jt = j; }
             }
             bt -= fabsf(z3.y) * toe_w + P.cfg.toe_margin;
             if (bt < best) { best = bt; jf = 8 + jt; }
