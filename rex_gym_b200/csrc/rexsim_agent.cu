@@ -118,11 +118,17 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
             h1[i] = fmaxf(s, 0.f);
         }
         __syncthreads();
-        float acc[RE][4];                               // layer 2 register tile
+        // layer 2 register tile, held as env PAIRS so the inner product runs on Blackwell's packed fp32x2 FMA (FFMA2, sm_100):
+        // acc2[p][j] = (env 2p, env 2p+1) x hidden unit j; per k one LDS.128 of weights, RE/4 LDS.128 of activations,
+        // 4 register moves to duplicate the weights and 2*RE FFMA2 (= 4*RE fp32 FMAs in half the issue slots)
+        float2 acc2[RE / 2][4];
         if (l2_active) {
             const float4 bb = ld4(b2 + 4 * og);
 #pragma unroll
-            for (int i = 0; i < RE; i++) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+            for (int p = 0; p < RE / 2; p++) {
+                acc2[p][0] = make_float2(bb.x, bb.x); acc2[p][1] = make_float2(bb.y, bb.y);
+                acc2[p][2] = make_float2(bb.z, bb.z); acc2[p][3] = make_float2(bb.w, bb.w);
+            }
             // thread's envs: chunk c (of RE/4) covers envs 64*c + 4*eg .. +3, so the 16 lanes of a half-warp read 256
             // contiguous bytes per LDS.128 (bank-conflict free; envs 8*eg .. 8*eg+7 would be a 4-way conflict)
             const float* hp = h1 + 4 * eg;
@@ -130,17 +136,24 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
 #pragma unroll 4
             for (int k = 0; k < H1; k++) {
                 const float4 w = ld4(wp);
-                float h[RE];
+                const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
 #pragma unroll
-                for (int i = 0; i < RE; i += 4) { const float4 t = ld4(hp + (i / 4) * 64); h[i] = t.x; h[i + 1] = t.y; h[i + 2] = t.z; h[i + 3] = t.w; }
-#pragma unroll
-                for (int i = 0; i < RE; i++) {
-                    acc[i][0] = fmaf(h[i], w.x, acc[i][0]); acc[i][1] = fmaf(h[i], w.y, acc[i][1]);
-                    acc[i][2] = fmaf(h[i], w.z, acc[i][2]); acc[i][3] = fmaf(h[i], w.w, acc[i][3]);
+                for (int cidx = 0; cidx < RE / 4; cidx++) {
+                    const float4 t = ld4(hp + cidx * 64);
+                    const float2 h01 = make_float2(t.x, t.y), h23 = make_float2(t.z, t.w);
+                    acc2[2 * cidx][0] = __ffma2_rn(h01, w0, acc2[2 * cidx][0]); acc2[2 * cidx][1] = __ffma2_rn(h01, w1, acc2[2 * cidx][1]);
+                    acc2[2 * cidx][2] = __ffma2_rn(h01, w2, acc2[2 * cidx][2]); acc2[2 * cidx][3] = __ffma2_rn(h01, w3, acc2[2 * cidx][3]);
+                    acc2[2 * cidx + 1][0] = __ffma2_rn(h23, w0, acc2[2 * cidx + 1][0]); acc2[2 * cidx + 1][1] = __ffma2_rn(h23, w1, acc2[2 * cidx + 1][1]);
+                    acc2[2 * cidx + 1][2] = __ffma2_rn(h23, w2, acc2[2 * cidx + 1][2]); acc2[2 * cidx + 1][3] = __ffma2_rn(h23, w3, acc2[2 * cidx + 1][3]);
                 }
                 hp += TM; wp += H2;
             }
         }
+        float acc[RE][4];                               // unpack: acc[i][j], i = 4*chunk + lane-in-chunk
+#pragma unroll
+        for (int p = 0; p < RE / 2; p++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { acc[2 * p][j] = acc2[p][j].x; acc[2 * p + 1][j] = acc2[p][j].y; }
         __syncthreads();                                // all reads of h1 done: reuse it for the head partials
         if (l2_active) {                                // head, part 1: this thread's 4 hidden units x its RE envs
             float w3[4][AG_MAX_A];
