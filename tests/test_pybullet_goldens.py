@@ -157,3 +157,32 @@ def test_wall_clock_gait_of_the_recorded_walk_ik_episodes():
         if d[0]:
             break
     assert big > 0.1                                                     # the nominal trot rocks the base 25x more
+
+
+def test_wall_clock_gait_of_the_recorded_gallop_ik_episodes():
+    """Same wall-clock effect on the gallop-ik policy's training data, where the observation also carries the 12 joint angles:
+    the recorded leg-joint ripple has a 7.0 control-step period (0.3 s gait period / 42 ms => the wall clock ran ~7.1x
+    faster than the simulation).  At gait_clock_scale = 8.5 (7-step cycle) the restatement reproduces period and size of the
+    joint-angle ripple (leg 0.059 rad, foot 0.046 rad recorded) -- IK-driven legs through the motor model at 24 Hz."""
+    ref = denorm(G["gallop_ik_observ"])
+    ac = G["gallop_ik_action"]
+    scale = 8.5      # phase step 6 ms * 8.5 / 0.3 s = 0.17 per control step: phi >= 0.99 after 6 steps, +1 step for the restart = 7
+    for ep in range(3):
+        s = OracleSim(1, "gallop", "ik", normalize=True, settle=2, target_position=2.0, gait_clock_scale=scale)
+        s.reset()
+        out = []
+        for t in range(400):
+            o, r, d = s.step(ac[ep, t][None, :])
+            assert not d[0], (ep, t)
+            out.append(denorm(o[0]))
+        out = np.array(out)
+
+        def period(x):
+            x = x - x.mean()
+            spec = np.abs(np.fft.rfft(x)); k = int(np.argmax(spec[5:])) + 5
+            return len(x) / k
+        assert abs(period(ref[ep, 101:401, 5]) - 7.0) < 0.5 and abs(period(out[100:, 5]) - 7.0) < 1.0
+        for j in (5, 6, 11, 12):                                       # leg / foot joints of a front and a rear leg
+            ours, real = out[100:, j].std(), ref[ep, 101:401, j].std()
+            assert 0.6 * real < ours < 1.6 * real, (ep, j, ours, real)
+        assert abs(out[100:, 1].mean() - ref[ep, 101:401, 1].mean()) < 0.03      # mean pitch of the hopping gait

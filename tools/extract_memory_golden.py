@@ -48,6 +48,10 @@ def main():
     v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ik")), ["memory/Variable_1", "memory/Variable_2"])
     out["walk_ik_action"] = v["memory/Variable_2"][:6, :300].astype(np.float32)
     out["walk_ik_observ"] = v["memory/Variable_1"][:6, :301].astype(np.float32)
+    # gallop-ik: same story (wall-clock gait), but the observation carries the 12 joint angles: 600 steps of 3 episodes
+    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "gallop", "ik")), ["memory/Variable_1", "memory/Variable_2"])
+    out["gallop_ik_action"] = v["memory/Variable_2"][:3, :600].astype(np.float32)
+    out["gallop_ik_observ"] = v["memory/Variable_1"][:3, :601].astype(np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
