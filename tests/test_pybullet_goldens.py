@@ -186,3 +186,30 @@ def test_wall_clock_gait_of_the_recorded_gallop_ik_episodes():
             ours, real = out[100:, j].std(), ref[ep, 101:401, j].std()
             assert 0.6 * real < ours < 1.6 * real, (ep, j, ours, real)
         assert abs(out[100:, 1].mean() - ref[ep, 101:401, 1].mean()) < 0.03      # mean pitch of the hopping gait
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rex_gym/policies"), reason="needs the shipped TF checkpoint (reference tree)")
+def test_shipped_gallop_policy_closes_the_loop_like_its_training_runs():
+    """End to end: the gallop-ol policy the reference ships (TF checkpoint -> pure-Python reader -> numpy restatement of
+    ForwardGaussianPolicy + StreamingNormalize) drives the restated simulator.  It gallops forward (-x) for the whole
+    1000-step episode, and its progress is consistent with the rewards PyBullet produced during training: the forward
+    reward is x / target with target ~ U(1, 3) (gallop_env.py:151, rex_gym_env.py:513-520), so every recorded reward implies
+    a target x_ours(t) / reward(t), which has to fall in that range if the two simulators cover ground at the same rate."""
+    from oracle import agent_oracle as AO
+    from rex_gym_b200.agents.networks import read_tf_policy
+    w, filt = read_tf_policy("/root/reference/rex_gym/policies/gallop/ol")
+    f = AO.StreamingNormalize((16,), True, True, 5)
+    f.count, f.mean, f.var_sum = filt[0], np.array(filt[1], np.float64), np.array(filt[2], np.float64)
+    s = OracleSim(1, "gallop", "ol", normalize=True, settle=2, target_position=2.0)
+    obs = s.reset()
+    e = s.env(0)
+    xs = []
+    for t in range(1000):
+        _, mean, _, _ = AO.perform(w, f, obs.astype(np.float64), False)
+        obs, r, d = s.step(mean.astype(np.float32))
+        xs.append(e.pos[0])
+        assert not d[0], t
+    xs = -np.array(xs)
+    assert 0.75 < xs[499] < 1.3 and 1.6 < xs[999] < 2.6 and abs(e.pos[1]) < 0.3          # ~0.35 m/s, straight
+    implied = xs[149] / G["gallop_ol_reward"][:, 149]                                       # recorded: sampled actions, 12 episodes
+    assert np.sum((implied > 0.85) & (implied < 3.5)) >= 10, implied
