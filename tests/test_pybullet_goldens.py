@@ -213,3 +213,30 @@ def test_shipped_gallop_policy_closes_the_loop_like_its_training_runs():
     assert 0.75 < xs[499] < 1.3 and 1.6 < xs[999] < 2.6 and abs(e.pos[1]) < 0.3          # ~0.35 m/s, straight
     implied = xs[149] / G["gallop_ol_reward"][:, 149]                                       # recorded: sampled actions, 12 episodes
     assert np.sum((implied > 0.85) & (implied < 3.5)) >= 10, implied
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rex_gym/policies"), reason="needs the shipped TF checkpoint (reference tree)")
+def test_shipped_walk_policy_reproduces_the_recorded_reward_profile():
+    """The shipped walk-ol policy in closed loop on the restated simulator, target 2.0 m: ramps up, walks to the goal, brakes
+    and stands still -- the per-step reward (rex_gym_env.py:501-542) has the profile of the 25 episodes PyBullet recorded in
+    the checkpoint: r(400)/r(200) in [3.8, 4.6] (acceleration phase), a final plateau of -0.28 ... -0.41 (the robot needs
+    0.3-0.4 m to stop past the goal: `tp - cx` once cx > tp + 0.15), and standing still for the rest of the 2000 steps."""
+    from oracle import agent_oracle as AO
+    from rex_gym_b200.agents.networks import read_tf_policy
+    w, filt = read_tf_policy("/root/reference/rex_gym/policies/walk/ol")
+    f = AO.StreamingNormalize((4,), True, True, 5)
+    f.count, f.mean, f.var_sum = filt[0], np.array(filt[1], np.float64), np.array(filt[2], np.float64)
+    s = OracleSim(1, "walk", "ol", normalize=True, settle=2, target_position=2.0, backwards=False)
+    obs = s.reset()
+    e = s.env(0)
+    R, X = [], []
+    for t in range(2000):
+        _, mean, _, _ = AO.perform(w, f, obs.astype(np.float64), False)
+        obs, r, d = s.step(mean.astype(np.float32))
+        R.append(float(r[0])); X.append(e.pos[0])
+        assert not d[0], t
+    R, X = np.array(R), -np.array(X)
+    assert 3.6 < R[400] / R[200] < 4.8                       # recorded: 3.76 ... 4.57
+    assert 0.9 < X[400] < 1.2                                # recorded r(400) = x / target, e.g. 0.96 at target ~1.1
+    assert -0.45 < R[-1] < -0.25 and abs(R[-1] - R[1200]) < 0.03      # recorded plateau: -0.414 ... -0.278, reached by step ~800
+    assert abs(X[-1] - X[1200]) < 0.02 and 2.2 < X[-1] < 2.5          # stands still past the goal
