@@ -119,7 +119,8 @@ int rexsim_step(RexSim* sim, const float* actions, float* obs, float* reward, ui
 /* Host-buffer form of rexsim_step -- BatchEnv.step with numpy arrays (batch_env.py:63-90): h_actions HOST [N][A] f32,
  * h_out HOST block of rexsim_host_out_bytes() bytes laid out as obs [N][O] f32 | reward [N] f32 | done [N] u8 | pad to 4 |
  * int32 OR of all error flags.  One call = H2D copy of the actions, the step kernel, one D2H copy of the results (+4 bytes of
- * flags) on `stream`, then a wait for that stream.  Pinned (page-locked) host memory gives the full copy speed. */
+ * flags) on `stream`, then a wait for that stream.  Pinned (page-locked) host memory gives the full copy speed; with pinned buffers
+ * and N <= 16384 the kernel addresses the host block directly (zero-copy) and the two bulk copies disappear. */
 int64_t rexsim_host_out_bytes(const RexSim* sim);
 int rexsim_step_host(RexSim* sim, const float* h_actions, void* h_out, void* stream);
 /* idx dev [k] int32 (NULL: all envs, k ignored); obs_out dev [k][O] or NULL */
