@@ -65,30 +65,14 @@ struct Params {
 // ----- tiny vector algebra ---------------------------------------------------------------------------
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-// Blackwell (sm_100) packed fp32x2 arithmetic: the (x, y) pair of a V3 goes through one FADD2 / FMUL2 / FFMA2 issue slot
-// (the scalar operand of s*a and fma3 is broadcast by the instruction itself), z stays scalar: 2 issue slots instead of 3.
-// Same IEEE round-to-nearest results as the scalar forms.
-#ifndef REXSIM_NO_F32X2
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return mk(r.x, r.y, a.z + b.z); }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y)); return mk(r.x, r.y, a.z - b.z); }
-__device__ __forceinline__ V3 operator*(float s, V3 a) { float2 r = __fmul2_rn(make_float2(s, s), make_float2(a.x, a.y)); return mk(r.x, r.y, s * a.z); }
-#else
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
-#endif
 __device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
     return mk(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
 }
-#ifndef REXSIM_NO_F32X2
-__device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) {
-    float2 r = __ffma2_rn(make_float2(s, s), make_float2(a.x, a.y), make_float2(b.x, b.y));
-    return mk(r.x, r.y, fmaf(s, a.z, b.z));
-}
-#else
 __device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) { return mk(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
-#endif
 struct M3 { V3 c0, c1, c2; };   // columns
 __device__ __forceinline__ V3 mul(const M3& R, V3 v) { return fma3(v.x, R.c0, fma3(v.y, R.c1, v.z * R.c2)); }
 struct SV { V3 a, l; };         // spatial vector: angular, linear
