@@ -28,7 +28,6 @@ struct RexSim {
     float* d_act = nullptr;            // staging for rexsim_step_host
     uint8_t* d_out = nullptr;          // obs | reward | done (same layout as the host block)
     int A = 0, O = 0;
-    const void* zc_act = nullptr; const void* zc_out = nullptr; bool zc_ok = false;   // rexsim_step_host: cached pointer attributes
     int nsnap = 1;
     int64_t launches = 0;
 };
@@ -179,11 +178,7 @@ int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* strea
     // Small batches with pinned buffers: the kernel reads the actions from, and writes its results into, the host block
     // directly (zero-copy over PCIe) -- two DMA launches and their latencies less than the staged form.  Large batches
     // stage through device buffers so the kernel never waits on PCIe.
-    if (h_actions != s->zc_act || h_out != s->zc_out) {          // pointer attributes are cached per buffer pair
-        s->zc_act = h_actions; s->zc_out = h_out;
-        s->zc_ok = device_can_address(h_actions) && device_can_address(h_out);
-    }
-    const bool zero_copy = s->zc_ok && N <= 16384;
+    const bool zero_copy = N <= 16384 && device_can_address(h_actions) && device_can_address(h_out);   // queried per call (~1 us)
     if (zero_copy) {
         P.actions = h_actions;
         P.obs = (float*)h_out; P.reward = (float*)h_out + N * s->O; P.done = (uint8_t*)h_out + out_done_offset(s);
