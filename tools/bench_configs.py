@@ -5,6 +5,7 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
 import rex_gym_b200 as R
+from bench import stagger_episodes
 
 CONFIGS = [
     ("C2 walk-ik flat 4096", dict(task="walk", num_envs=4096, signal_type="ik", target_position=2.0, backwards=False)),
@@ -24,6 +25,7 @@ def main():
         env.reset()
         n = env.num_envs
         acts = torch.rand((30, n, env.action_dim), device="cuda") * 2 - 1
+        stagger_episodes(env, acts)          # de-synchronised episode phases, as under auto-reset (see bench.py)
         for k in range(20): env.step(acts[k % 30])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
