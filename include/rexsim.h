@@ -123,6 +123,12 @@ int rexsim_step(RexSim* sim, const float* actions, float* obs, float* reward, ui
  * and N <= 16384 the kernel addresses the host block directly (zero-copy) and the two bulk copies disappear. */
 int64_t rexsim_host_out_bytes(const RexSim* sim);
 int rexsim_step_host(RexSim* sim, const float* h_actions, void* h_out, void* stream);
+/* Re-group the environments over the warps by the solver cost of their last control step (counting sort on the device, three
+ * small launches).  The step kernel's cost per env is dominated by its PGS iteration count, and a warp of 8 envs runs as long
+ * as its slowest one; in a de-synchronised batch (auto-reset) grouping envs of similar cost recovers most of that loss.
+ * Purely a scheduling hint: every env's results are bit-identical with and without it.  Call every few steps (the
+ * Python mirror does it every 8). */
+int rexsim_rebalance(RexSim* sim, void* stream);
 /* idx dev [k] int32 (NULL: all envs, k ignored); obs_out dev [k][O] or NULL */
 int rexsim_reset(RexSim* sim, const int32_t* idx, int32_t k, float* obs_out, void* stream);
 

@@ -37,7 +37,7 @@ AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_cr
                  "rexagent_lambda_advantage", "rexagent_gae_segments", "rexagent_launch_count"]
 
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
-           "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
+           "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_rebalance", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
            "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
 
 _LIB = None
@@ -66,6 +66,7 @@ def load():
     L.rexsim_step_host.argtypes = [C.c_void_p] * 4
     L.rexsim_host_out_bytes.argtypes = [C.c_void_p]
     L.rexsim_host_out_bytes.restype = C.c_int64
+    L.rexsim_rebalance.argtypes = [C.c_void_p, C.c_void_p]
     L.rexsim_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.rexsim_get_state.argtypes = [C.c_void_p] * 4
     L.rexsim_set_state.argtypes = [C.c_void_p] * 3

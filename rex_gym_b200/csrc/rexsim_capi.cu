@@ -11,6 +11,7 @@ cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st);
 cudaError_t launch_settle(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st);
 cudaError_t launch_get_state(const Params& P, float* out_f, int32_t* out_i, cudaStream_t st);
 cudaError_t launch_set_state(const Params& P, const float* in_f, cudaStream_t st);
+cudaError_t launch_rebalance(const int32_t* cost, int n, int32_t* hist, int32_t* perm, cudaStream_t st);
 }  // namespace rexsim
 
 using namespace rexsim;
@@ -25,6 +26,10 @@ struct RexSim {
     float* d_zoff = nullptr;
     int32_t* d_err = nullptr;
     float* d_cmd = nullptr;
+    int32_t* d_perm = nullptr;         // slot -> env, sorted by solver cost (rexsim_rebalance)
+    int32_t* d_cost = nullptr;
+    int32_t* d_hist = nullptr;
+    bool perm_valid = false;
     float* d_act = nullptr;            // staging for rexsim_step_host
     uint8_t* d_out = nullptr;          // obs | reward | done (same layout as the host block)
     int A = 0, O = 0;
@@ -109,6 +114,10 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     CK(cudaMemset(s->d_err, 0, (size_t)(N + 1) * sizeof(int32_t)));
     CK(cudaMalloc(&s->d_cmd, (size_t)12 * N * sizeof(float)));
     CK(cudaMemset(s->d_cmd, 0, (size_t)12 * N * sizeof(float)));
+    CK(cudaMalloc(&s->d_perm, (size_t)N * sizeof(int32_t)));
+    CK(cudaMalloc(&s->d_cost, (size_t)N * sizeof(int32_t)));
+    CK(cudaMemset(s->d_cost, 0, (size_t)N * sizeof(int32_t)));
+    CK(cudaMalloc(&s->d_hist, 256 * sizeof(int32_t)));
     s->A = rexsim_action_dim(cfg->task, cfg->signal); s->O = rexsim_obs_dim(cfg->task, cfg->num_motors);
     CK(cudaMalloc(&s->d_act, (size_t)N * s->A * sizeof(float)));
     CK(cudaMalloc(&s->d_out, (size_t)rexsim_host_out_bytes(s)));
@@ -128,6 +137,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     s->P.model = s->d_model; s->P.sf = s->d_sf; s->P.si = s->d_si;
     s->P.snap_f = s->d_snap_f; s->P.snap_i = s->d_snap_i; s->P.field_zoff = s->d_zoff;
     s->P.err = s->d_err; s->P.cmd_out = s->d_cmd;
+    s->P.cost = s->d_cost; s->P.perm = nullptr;
     // settled reset snapshots: Rex.Reset's 100 + 0.5/dt holding sub-steps (rex.py:314-323), once per field
     for (int f = 0; f < s->nsnap; f++) {
         s->P.settle_snapshot = f;
@@ -144,7 +154,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
 void rexsim_destroy(RexSim* s) {
     if (!s) return;
     cudaFree(s->d_model); cudaFree(s->d_sf); cudaFree(s->d_si); cudaFree(s->d_snap_f); cudaFree(s->d_snap_i);
-    cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd); cudaFree(s->d_act); cudaFree(s->d_out);
+    cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd); cudaFree(s->d_act); cudaFree(s->d_out); cudaFree(s->d_perm); cudaFree(s->d_cost); cudaFree(s->d_hist);
     delete s;
 }
 
@@ -193,6 +203,15 @@ int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* strea
     if (!zero_copy) CK(cudaMemcpyAsync(h_out, s->d_out, out_err_offset(s), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((char*)h_out + out_err_offset(s), s->d_err + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return REXSIM_OK;
+}
+
+int rexsim_rebalance(RexSim* s, void* stream) {
+    if (!s) return fail(REXSIM_ERR_INVALID, "null handle");
+    cudaError_t e = launch_rebalance(s->d_cost, s->P.N, s->d_hist, s->d_perm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "rebalance launch");
+    s->launches += 3;
+    s->P.perm = s->d_perm;              // steps enqueued after this call use the new grouping
     return REXSIM_OK;
 }
 

@@ -51,6 +51,7 @@ struct Lane {
     uint32_t enabled;      // 3 bits
     int contact;           // own toe in contact during the last sub-step
     int err;
+    int cost;              // solver iterations spent this control step (drives the warp re-grouping, rexsim_rebalance)
 };
 
 __device__ __forceinline__ M3 quat_to_mat(float x, float y, float z, float w) {   // btMatrix3x3::setRotation
@@ -579,6 +580,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         bool running = true;             // env-uniform: the 4 lanes of an env leave the loop together
         const bool mine = active;
         for (int it = 0; it < iters && running; it++) {
+            L.cost++;
             float resid = 0.f;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
@@ -739,6 +741,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         }
         bool running = true;
         for (int it = 0; it < iters && running; it++) {
+            L.cost++;
             float resid = 0.f;
 #pragma unroll 1
             for (int tt = 0; tt < nl + nc; tt++) {
@@ -1128,7 +1131,7 @@ __device__ __forceinline__ void load_lane(const float* sf, const int32_t* si, in
     }
     L.ovh = (uint32_t)si[(I_OVH + leg) * (size_t)N + env];
     L.enabled = ((uint32_t)si[I_FLAGS * (size_t)N + env] >> (FL_ENABLED_SHIFT + 3 * leg)) & 7u;
-    L.contact = 0; L.err = 0;
+    L.contact = 0; L.err = 0; L.cost = 0;
 }
 __device__ __forceinline__ void load_task(const float* sf, const int32_t* si, int N, int env, Task& K) {
     K.step_counter = si[I_STEP * (size_t)N + env];
@@ -1301,10 +1304,14 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
 
     const int N = P.N;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    int env = gid >> 2;
+    int slot = gid >> 2;
     const int leg = gid & 3;
-    const bool valid = env < N;
-    if (!valid) env = N - 1;          // keep the warp converged for the shuffles; stores are masked
+    const bool valid = slot < N;
+    if (!valid) slot = N - 1;         // keep the warp converged for the shuffles; stores are masked
+    // Warp re-grouping: slot -> env through a permutation sorted by last step's solver cost (rexsim_rebalance), so the 8
+    // envs of a warp need about the same number of PGS iterations.  Every env's arithmetic is independent of the
+    // permutation (bit-identical results); the scattered state accesses stay in L2.
+    const int env = P.perm ? P.perm[slot] : slot;
     const RexSimConfig& c = P.cfg;
     constexpr int A = (TASK == REXSIM_TASK_WALK) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 8)
                     : (TASK == REXSIM_TASK_GALLOP) ? (SIGNAL == REXSIM_SIGNAL_IK ? 2 : 4)
@@ -1397,6 +1404,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     if (!finite) { L.err |= REXSIM_FLAG_NONFINITE; done = true; }
     int err = (int)or4((unsigned)L.err);
     if (valid && leg == 0) {
+        if (P.cost) P.cost[env] = L.cost;
         P.reward[env] = reward;
         P.done[env] = done ? 1 : 0;
         if (err) { P.err[env] |= err; atomicOr(&P.err[N], err); }
@@ -1446,7 +1454,7 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     L.pos = mk(0.f, 0.f, 0.21f); L.qx = 0.f; L.qy = 0.f; L.qz = 0.f; L.qw = 1.f;
     L.vl = mk(0, 0, 0); L.w = mk(0, 0, 0);
     for (int j = 0; j < 3; j++) { L.q[j] = c_pose_stand[j]; L.qd[j] = 0.f; L.tau_obs[j] = 0.f; }
-    L.ovh = 0u; L.enabled = 7u; L.contact = 0; L.err = 0;
+    L.ovh = 0u; L.enabled = 7u; L.contact = 0; L.err = 0; L.cost = 0;
     Arm AR;
     if (ARM) {
 #pragma unroll
@@ -1571,6 +1579,32 @@ __global__ void set_state_kernel(const Params P, const float* in_f) {
         P.sf[(j < 12 ? F_Q + j : F_AQ + j - 12) * N + env] = in_f[(13 + j) * N + env];
         P.sf[(j < 12 ? F_QD + j : F_AQD + j - 12) * N + env] = in_f[(13 + nm + j) * N + env];
     }
+}
+
+// ---- warp re-grouping: counting sort of the envs by solver cost, most expensive first (they start first: LPT order) ----
+__global__ void rebalance_hist_kernel(const int32_t* __restrict__ cost, int n, int32_t* __restrict__ hist) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) atomicAdd(&hist[255 - min(cost[e] >> 1, 255)], 1);
+}
+__global__ void rebalance_scan_kernel(int32_t* hist) {          // 1 block, 256 threads: exclusive prefix sum in place
+    __shared__ int32_t s[256];
+    const int t = threadIdx.x;
+    s[t] = hist[t];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) { int v = t >= o ? s[t - o] : 0; __syncthreads(); s[t] += v; __syncthreads(); }
+    hist[t] = s[t] - hist[t];
+}
+__global__ void rebalance_scatter_kernel(const int32_t* __restrict__ cost, int n, int32_t* __restrict__ offs, int32_t* __restrict__ perm) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) perm[atomicAdd(&offs[255 - min(cost[e] >> 1, 255)], 1)] = e;
+}
+cudaError_t launch_rebalance(const int32_t* cost, int n, int32_t* hist, int32_t* perm, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, 256 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    rebalance_hist_kernel<<<(n + 255) / 256, 256, 0, st>>>(cost, n, hist);
+    rebalance_scan_kernel<<<1, 256, 0, st>>>(hist);
+    rebalance_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(cost, n, hist, perm);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_step_unit_0(const Params&, cudaStream_t);

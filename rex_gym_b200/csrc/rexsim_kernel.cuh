@@ -60,6 +60,8 @@ struct Params {
     int32_t settle_snapshot;           // settle kernel: which snapshot this launch produces
     int32_t N;
     int32_t sm_count;                  // SMs of the device (kernel variant choice)
+    const int32_t* __restrict__ perm;  // [N] slot -> env (null: identity); see rexsim_rebalance
+    int32_t* __restrict__ cost;        // [N] solver iterations of the last control step
 };
 
 // ----- tiny vector algebra ---------------------------------------------------------------------------

@@ -78,7 +78,8 @@ class BatchedRexEnv(object):
                  energy_weight=None, signal_type="ik", terrain_type="plane", terrain_id=None, mark="base",
                  normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
                  motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0,
-                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, gait_clock_scale=1.0):
+                 base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, gait_clock_scale=1.0,
+                 rebalance_every=8):
         if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
             raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
         if task not in TASKS or signal_type not in SIGNALS:
@@ -185,6 +186,10 @@ class BatchedRexEnv(object):
             ub = np.full(O, 2 * math.pi, np.float32)
             ub[2:4] = 2 * math.pi / self._time_step
             self.observation_space = Box(-(ub + OBSERVATION_EPS), ub + OBSERVATION_EPS)
+        # every `rebalance_every` steps the envs are re-grouped over the warps by solver cost (rexsim_rebalance): a scheduling
+        # hint only -- results are bit-identical with 0 (off); pays off in de-synchronised batches of >= a few thousand envs
+        self._rebalance_every = int(rebalance_every) if self.num_envs >= 1024 else 0
+        self._nsteps = 0
         self._closed = False
 
     # ---- BatchEnv surface ------------------------------------------------------------------------
@@ -198,6 +203,12 @@ class BatchedRexEnv(object):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _maybe_rebalance(self):
+        self._nsteps += 1
+        if self._rebalance_every and self._nsteps % self._rebalance_every == 0:
+            with torch.cuda.device(self.device):
+                _capi.check(self._L.rexsim_rebalance(self._h, self._stream()))
 
     def step(self, action):
         """BatchEnv.step (batch_env.py:63-90).  numpy in -> numpy out (host buffers: one rexsim_step_host call = H2D copy,
@@ -217,6 +228,7 @@ class BatchedRexEnv(object):
                                          self._done_u8.data_ptr(), torch.cuda.current_stream().cuda_stream)
             if rc:
                 _capi.check(rc)
+            self._maybe_rebalance()
             return self._obs, self._reward, self._done, _Info(self)
         a = np.asarray(action, dtype=np.float32)
         if a.shape != (N, A):
@@ -231,6 +243,7 @@ class BatchedRexEnv(object):
             rc = self._L.rexsim_step_host(self._h, self._h_act_ptr, self._h_out_ptr, torch.cuda.current_stream().cuda_stream)
         if rc:
             _capi.check(rc)
+        self._maybe_rebalance()
         if self._h_err[0] & ERR_NONFINITE:
             raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
         return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), _Info(self)
@@ -240,6 +253,7 @@ class BatchedRexEnv(object):
         written into the caller's contiguous CUDA buffers (e.g. slices of a rollout).  One asynchronous kernel launch."""
         with torch.cuda.device(self.device):
             _capi.check(self._L.rexsim_step(self._h, action.data_ptr(), obs.data_ptr(), reward.data_ptr(), done_u8.data_ptr(), self._stream()))
+        self._maybe_rebalance()
 
     def reset(self, indices=None):
         """BatchEnv.reset (batch_env.py:92-109): observations of the reset environments."""

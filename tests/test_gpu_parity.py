@@ -428,3 +428,25 @@ def test_cuda_path_tracks_pybullet_goldens(task):
         assert np.median(rp.max(1)) < 4.5e-3 and np.median(rp.mean(1)) < 1.5e-3
     assert env.check_errors() == 0
     env.close()
+
+
+def test_warp_regrouping_does_not_change_any_result():
+    """rexsim_rebalance re-groups the envs over the warps by solver cost; each env's arithmetic is independent of where it
+    runs, so a de-synchronised batch stepped with re-grouping every step and one without give bit-identical outputs and state."""
+    n = 4096
+    kw = dict(signal_type="ik", normalize=True, auto_reset=True, max_episode_steps=60, seed=21)
+    a, b = _env("walk", n, rebalance_every=1, **kw), _env("walk", n, rebalance_every=0, **kw)
+    a.reset(); b.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for k in range(90):
+        act = torch.rand((n, 2), device="cuda", generator=gen) * 2 - 1
+        if k % 7 == 3:                                        # stagger the episode phases
+            idx = torch.randperm(n, device="cuda", generator=gen)[:n // 5].to(torch.int32)
+            a.reset(idx); b.reset(idx)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), k
+    assert torch.equal(a._state_f, b._state_f) and torch.equal(a._state_i, b._state_i)
+    perm = torch.as_tensor(a._L.rexsim_launch_count(a._h))     # the re-grouping did run
+    assert int(perm) > int(b._L.rexsim_launch_count(b._h))
+    a.close(); b.close()
