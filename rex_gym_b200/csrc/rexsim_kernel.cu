@@ -634,6 +634,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         if (ARM && leg == 0) { float z6[ARM_NJ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; arm_apply(AR, dv0, z6, dqA); }
     }
     else if (envf & 2u) {
+        L.cost += 64;      // the generic path is several times the fast path: such envs sort together (rexsim_rebalance)
         // ================= generic path: body contacts and/or a joint limit ====================================
         // M^-1 of a star-shaped tree = per-leg block + a rank-6 coupling through the base, so no Delassus matrix is
         // needed: a row's velocity is  J_r dV = -g_r . beta + Jq_r . eps  with beta = base velocity change (replicated
