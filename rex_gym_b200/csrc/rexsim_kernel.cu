@@ -579,13 +579,11 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         float lam[3] = {0.f, 0.f, 0.f}, rs[3] = {0.f, 0.f, 0.f};
         bool running = true;             // env-uniform: the 4 lanes of an env leave the loop together
         const bool mine = active;
-        const unsigned cm = or4(active ? (1u << leg) : 0u);    // env-uniform: which legs have a contact this sub-step
         for (int it = 0; it < iters && running; it++) {
             L.cost++;
             float resid = 0.f;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                if (!(cm & (1u << s))) continue;      // leg s has no contact: its round would broadcast a zero change
                 float dI = rhs[0] - rs[0] * dinv[0];
                 if (lam[0] + dI < 0.f) dI = -lam[0];
                 const bool upd = mine && running && (leg == s);
@@ -599,7 +597,6 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             for (int s = 0; s < 4; s++) {
                 // both friction rows of contact s belong to lane s: update t1, fold its change into the own t2 sum
                 // locally, update t2, then broadcast the two changes together (one communication round per contact)
-                if (!(cm & (1u << s))) continue;
                 const float lim = mu * lam[0];
                 const bool upd = mine && running && (leg == s) && (lam[0] > 0.f);
                 float dI1 = rhs[1] - rs[1] * dinv[1];
@@ -1407,9 +1404,8 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     finite = (sum4(finite ? 0.f : 1.f) == 0.f);
     if (!finite) { L.err |= REXSIM_FLAG_NONFINITE; done = true; }
     int err = (int)or4((unsigned)L.err);
-    const unsigned cmask = or4(((unsigned)L.contact & 1u) << leg);       // feet on the ground in the last sub-step
     if (valid && leg == 0) {
-        if (P.cost) P.cost[env] = L.cost | (int)(cmask << 12);
+        if (P.cost) P.cost[env] = L.cost;
         P.reward[env] = reward;
         P.done[env] = done ? 1 : 0;
         if (err) { P.err[env] |= err; atomicOr(&P.err[N], err); }
@@ -1587,12 +1583,9 @@ __global__ void set_state_kernel(const Params P, const float* in_f) {
 }
 
 // ---- warp re-grouping: counting sort of the envs by solver cost, most expensive first (they start first: LPT order) ----
-// key: feet-on-the-ground mask (the PGS skips the rounds of legs without contact, so envs of one warp should agree on it),
-// then the solver iterations in 16 levels; most expensive first
-__device__ __forceinline__ int rebalance_bucket(int c) { return 255 - ((((c >> 12) & 15) << 4) | min((c & 4095) >> 4, 15)); }
 __global__ void rebalance_hist_kernel(const int32_t* __restrict__ cost, int n, int32_t* __restrict__ hist) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) atomicAdd(&hist[rebalance_bucket(cost[e])], 1);
+    if (e < n) atomicAdd(&hist[255 - min(cost[e] >> 1, 255)], 1);
 }
 __global__ void rebalance_scan_kernel(int32_t* hist) {          // 1 block, 256 threads: exclusive prefix sum in place
     __shared__ int32_t s[256];
@@ -1604,7 +1597,7 @@ __global__ void rebalance_scan_kernel(int32_t* hist) {          // 1 block, 256 
 }
 __global__ void rebalance_scatter_kernel(const int32_t* __restrict__ cost, int n, int32_t* __restrict__ offs, int32_t* __restrict__ perm) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) perm[atomicAdd(&offs[rebalance_bucket(cost[e])], 1)] = e;
+    if (e < n) perm[atomicAdd(&offs[255 - min(cost[e] >> 1, 255)], 1)] = e;
 }
 cudaError_t launch_rebalance(const int32_t* cost, int n, int32_t* hist, int32_t* perm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(hist, 0, 256 * sizeof(int32_t), st);
