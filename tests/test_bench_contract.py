@@ -1,0 +1,44 @@
+"""bench.py contract: one JSON line with the keys the driver reads.  The reference arm (CPU, oracle port) runs anywhere; the
+GPU arm is checked on the GPU box with a handful of steps."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(*args):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_the_contract_line():
+    j = _run("--impl", "reference", "--steps", "4", "--warmup", "1")
+    assert BASE_KEYS <= set(j) and j["impl"] == "reference" and j["metric"] == "env-steps/sec" and j["unit"] == "env-steps/s"
+    assert j["value"] > 0 and j["higher_is_better"] is True and j["vs_baseline"] is None and j["dtype"] == "f64"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"]
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    j = _run("--steps", "6", "--warmup", "3")
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(j)
+    assert j["n_gpus"] == 1 and j["steps"] == 6 and j["warmup"] == 3 and j["gpu_launches"] == 6 and j["dtype"] == "f32" and j["scaling"] == "weak"
+    assert j["value"] > 1e6 and abs(j["ms_per_step"] * 1e-3 * j["value"] - j["config"]["envs_per_gpu"]) < 1e-3 * j["config"]["envs_per_gpu"]
+    rf = j["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"] > 0
+    assert j["e2e"]["value"] > 1e6 and j["e2e"]["h2d_bytes_per_step"] == 4096 * 2 * 4 and j["e2e"]["d2h_bytes_per_step"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] > 1e3
+    assert j["config"]["error_flags_or"] == 0 and j["config"]["north_star_size"]["error_flags_or"] == 0
+    assert "error" not in j["config"]["rollout_with_policy"]
