@@ -41,5 +41,7 @@ def test_gpu_arm_prints_the_contract_line():
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"] > 0
     assert j["e2e"]["value"] > 1e6 and j["e2e"]["h2d_bytes_per_step"] == 4096 * 2 * 4 and j["e2e"]["d2h_bytes_per_step"] > 0
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] > 1e3
-    assert j["config"]["error_flags_or"] == 0 and j["config"]["north_star_size"]["error_flags_or"] == 0
+    ns = j["config"]["north_star_size"]
+    assert j["config"]["error_flags_or"] == 0 and ns["error_flags_or"] == 0 and ns["envs_per_gpu"] == 65536 and ns["value"] > 1e7
+    assert ns["training_clock_x16"]["error_flags_or"] == 0 and ns["training_clock_x16"]["value"] > 1e7
     assert "error" not in j["config"]["rollout_with_policy"]
