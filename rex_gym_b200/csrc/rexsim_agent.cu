@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
         }
         __syncthreads();
         // layer 2 register tile, held as env PAIRS so the inner product runs on Blackwell's packed fp32x2 FMA (FFMA2, sm_100):
-        // acc2[p][j] = (env 2p, env 2p+1) x hidden unit j; per k one LDS.128 of weights, RE/4 LDS.128 of activations,
-        // 4 register moves to duplicate the weights and 2*RE FFMA2 (= 4*RE fp32 FMAs in half the issue slots)
+        // acc2[p][j] = (env 2p, env 2p+1) x hidden unit j; per k one LDS.128 of weights, RE/4 LDS.128 of activations and
+        // 2*RE FFMA2 (= 4*RE fp32 FMAs in half the issue slots; the weight is the instruction's scalar-broadcast operand)
         float2 acc2[RE / 2][4];
         if (l2_active) {
             const float4 bb = ld4(b2 + 4 * og);
