@@ -127,7 +127,7 @@ int rexsim_step_host(RexSim* sim, const float* h_actions, void* h_out, void* str
  * small launches).  The step kernel's cost per env is dominated by its PGS iteration count, and a warp of 8 envs runs as long
  * as its slowest one; in a de-synchronised batch (auto-reset) grouping envs of similar cost recovers most of that loss.
  * Purely a scheduling hint: every env's results are bit-identical with and without it.  Call every few steps (the
- * Python mirror does it every 8). */
+ * Python mirror does it every 8 for batches of >= 8192 envs; a batch that fits one wave gains nothing). */
 int rexsim_rebalance(RexSim* sim, void* stream);
 /* idx dev [k] int32 (NULL: all envs, k ignored); obs_out dev [k][O] or NULL */
 int rexsim_reset(RexSim* sim, const int32_t* idx, int32_t k, float* obs_out, void* stream);

@@ -187,8 +187,9 @@ class BatchedRexEnv(object):
             ub[2:4] = 2 * math.pi / self._time_step
             self.observation_space = Box(-(ub + OBSERVATION_EPS), ub + OBSERVATION_EPS)
         # every `rebalance_every` steps the envs are re-grouped over the warps by solver cost (rexsim_rebalance): a scheduling
-        # hint only -- results are bit-identical with 0 (off); pays off in de-synchronised batches of >= a few thousand envs
-        self._rebalance_every = int(rebalance_every) if self.num_envs >= 1024 else 0
+        # hint only -- results are bit-identical with 0 (off).  It pays off once the batch is several waves deep (+17-19 % at
+        # 16 384 / 65 536 envs); a batch that fits one wave (4096 envs = 128 CTAs on 148 SMs) is bound by its slowest env anyway
+        self._rebalance_every = int(rebalance_every) if self.num_envs >= 8192 else 0
         self._nsteps = 0
         self._closed = False
 
