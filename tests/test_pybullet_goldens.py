@@ -81,6 +81,37 @@ def test_walk_open_loop_tracks_pybullet():
     assert np.median(rp.mean(1)) < 1.5e-3
 
 
+def _standup_replay(ep, steps):
+    ac, ref, rw = G["standup_ol_action"][ep], denorm(G["standup_ol_observ"][ep]), G["standup_ol_reward"][ep]
+    s = OracleSim(1, "standup", "ol", normalize=True)              # the full reset hold (rex.py:314-323), not the pristine pose
+    s.reset()
+    P, R = [], []
+    for t in range(steps):
+        o, r, _ = s.step(ac[t][None, :])
+        P.append(denorm(o[0])[1]); R.append(r[0])
+    return np.array(P), np.array(R), ref[1:steps + 1, 1], rw[:steps]
+
+
+def test_standup_hop_tracks_pybullet_through_the_first_30_steps():
+    """Standup episodes start from the belly-down rest pose the reset hold ends in, so they cannot be replayed from a pristine
+    state; from our own hold the hop off the folded legs (first 30 control steps = 150 sub-steps, open loop) tracks the
+    recorded pitch within 0.045 rad and crosses |pos - target| = 0.1 (reward sign flip) within one control step of PyBullet."""
+    err, flip = [], []
+    for ep in range(EPISODES):
+        P, R, pref, rref = _standup_replay(ep, 30)
+        err.append(np.abs(P - pref).max())
+        flip.append(abs(int(np.argmax(R > 0)) - int(np.argmax(rref > 0))))
+    assert np.median(err) < 0.045 and max(err) < 0.06
+    assert max(flip) <= 1
+
+
+@pytest.mark.xfail(reason="DESIGN.md section 9: PyBullet's reset hold ends belly-down (z ~ 0.039, feet past the 2.59 rad limit), "
+                          "ours on the toes (z 0.0657); first reward -0.160 vs -0.184", strict=False)
+def test_standup_rest_pose_matches_the_recorded_first_reward():
+    _, R, _, rref = _standup_replay(0, 1)
+    assert abs(R[0] - rref[0]) < 5e-3
+
+
 def _with_cfg(task, ep, **ov):
     """Replay with overridden physics constants (friction etc.)."""
     import ctypes as C
