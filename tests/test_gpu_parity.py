@@ -430,6 +430,31 @@ def test_cuda_path_tracks_pybullet_goldens(task):
     env.close()
 
 
+def test_cuda_standup_hop_tracks_pybullet_goldens():
+    """Standup episodes start from the reset hold's rest pose, so they run from the CUDA path's own settle: the hop off the
+    folded legs (first 30 control steps, stored actions, open loop) against the recorded pitch and reward sign flip
+    (oracle counterpart and the known rest-pose gap: tests/test_pybullet_goldens.py)."""
+    import math
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pybullet_memory_golden.npz"))
+    ua = 2 * math.pi + 0.01
+    n, steps = 12, 30
+    ac, ref, rw = G["standup_ol_action"][:n], G["standup_ol_observ"][:n].astype(np.float64) * ua, G["standup_ol_reward"][:n]
+    env = _env("standup", n, signal_type="ol", normalize=True)
+    env.reset()
+    err, R = np.zeros((n, steps)), np.zeros((n, steps))
+    for t in range(steps):
+        o, r, d, _ = env.step(ac[:, t])
+        err[:, t] = np.abs(np.asarray(o, np.float64)[:, 1] * ua - ref[:, t + 1, 1])
+        R[:, t] = r
+        assert not d.any()
+    assert np.median(err.max(1)) < 0.05 and err.max() < 0.07
+    flip = np.abs(np.argmax(R > 0, 1) - np.argmax(rw[:, :steps] > 0, 1))
+    assert flip.max() <= 1
+    assert env.check_errors() == 0
+    env.close()
+
+
 def test_warp_regrouping_does_not_change_any_result():
     """rexsim_rebalance re-groups the envs over the warps by solver cost; each env's arithmetic is independent of where it
     runs, so a de-synchronised batch stepped with re-grouping every step and one without give bit-identical outputs and state."""
