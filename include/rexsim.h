@@ -53,6 +53,7 @@ enum {
     REXSIM_FLAG_JOINT_LIMIT = 2,      /* more than one joint limit violated in one leg: only one limit row per leg is modelled */
     REXSIM_FLAG_BODY_CONTACT = 4,     /* reserved (body contacts are solved since the generic row path exists) */
     REXSIM_FLAG_TILE_MISS = 8,        /* a contact query fell outside the 0.8 m heightfield window staged in shared memory */
+    REXSIM_FLAG_BAD_INDEX = 16,       /* rexsim_reset saw an index outside [0, N): skipped (aggregate word only) */
 };
 
 #define REXSIM_MAX_TOE_PTS 96
@@ -92,7 +93,10 @@ typedef struct {
     float residual_threshold;         /* solver early-out (pybullet default 1e-7) */
     float erp_contact, erp_joint;
     int32_t toe_npts;                 /* profile vertices of the toe prism in the model table */
-    float toe_margin;
+    float toe_margin;                 /* added to the toe hull's reach [m]; -0.25 mm: identified on the recorded PyBullet touchdown */
+    float contact_breaking;           /* manifold breaking distance: a contact row exists while the distance is below it (0.64 mm) */
+    float link_damping;               /* btMultiBody m_linearDamping = m_angularDamping (0.04), applied to every link */
+    float max_coordinate_velocity;    /* btMultiBody m_maxCoordinateVelocity (100): clamp on all generalised velocities */
     int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */
     double gait_clock_scale;          /* GaitPlanner clock = simulation time x this.  1 = the deterministic simulation clock (DESIGN.md
                                        * section 2).  The reference reads the WALL clock (gait_planner.py:108-110); the walk-ik episodes stored
@@ -140,8 +144,11 @@ int rexsim_get_state(RexSim* sim, float* out_f, int32_t* out_i, void* stream);
 int rexsim_set_state(RexSim* sim, const float* in_f, void* stream);
 /* raw SoA state for checkpoint/resume: [n_float][N] f32 and [n_int][N] i32 device buffers */
 int rexsim_state_buffers(RexSim* sim, float** state_f, int32_t** state_i);
-/* dev [N + 1] int32: per-env error bits, then one word holding the OR of all; never cleared by the library */
+/* dev [N + 1] int32: word e = error bits of env e's most recent step (cleared by a reset of that env); word N = OR of every
+ * bit raised since it was last cleared.  rexsim_step_host clears the aggregate after copying it out (per-step semantics, like
+ * ConvertTo32Bit raising for the offending step only, wrappers.py:522-543); device-path callers use rexsim_clear_errors. */
 int rexsim_error_flags(RexSim* sim, int32_t** err_flags);
+int rexsim_clear_errors(RexSim* sim, void* stream);          /* zeroes the aggregate word (enqueued on stream) */
 /* last motor command of every env (info['action'], rex_gym_env.py:414): dev [nm][N] */
 int rexsim_last_command(RexSim* sim, float** cmd);
 /* kernels launched by this handle since create (the bench reports it) */

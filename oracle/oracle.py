@@ -47,7 +47,9 @@ class RexoConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("seed", C.c_uint64),
         ("nfields", C.c_int32), ("fields", C.POINTER(C.c_float)), ("friction", C.c_double),
         ("residual_threshold", C.c_double), ("erp_contact", C.c_double), ("erp_joint", C.c_double),
-        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("gait_clock_scale", C.c_double), ("pose_values", C.c_double * 5),
+        ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("gait_clock_scale", C.c_double),
+        ("link_damping", C.c_double), ("contact_breaking", C.c_double),
+        ("max_coordinate_velocity", C.c_double), ("pose_values", C.c_double * 5),
     ]
 
 
@@ -118,7 +120,7 @@ def _rpy_to_mat(rpy):
 # trajectories recovered from the reference's checkpoints (tests/golden/pybullet_memory_golden.npz) put the touchdown of a
 # robot dropped from z = 0.21 where the EXACT hull without margin reaches the ground (1 mm of margin lands one control step
 # early in all 12 episodes; tools/dev_pybullet_replay.py), so the restatement uses 0.
-TOE_MARGIN = float(os.environ.get("REXO_TOE_MARGIN", 0.0))
+TOE_MARGIN = float(os.environ.get("REXO_TOE_MARGIN", -0.00025))     # rex_gym_b200/model_tables.py TOE_MARGIN (same constant, same reason)
 
 
 def load_model(mark="base", toes_only=False, terrain_full_toe=False):
@@ -199,7 +201,8 @@ class OracleSim:
                  max_episode_steps=0, seed=1234, nfields=0, fields=None, toes_only=False, settle=True,
                  solver_iterations=None, residual_threshold=1e-7, env_offset=0,
                  base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, terrain_full_toe=False,
-                 gait_clock_scale=1.0):
+                 gait_clock_scale=1.0, max_coordinate_velocity=100.0,
+                 link_damping=0.04, contact_breaking=None):
         self.L = lib(f32)
         self.model, self.model_json = load_model(mark, toes_only=toes_only, terrain_full_toe=terrain_full_toe)
         c = RexoConfig()
@@ -235,6 +238,12 @@ class OracleSim:
         c.settle_on_reset = int(settle)
         c.env_offset = int(env_offset)
         c.gait_clock_scale = float(gait_clock_scale)
+        c.max_coordinate_velocity = float(max_coordinate_velocity)
+        c.link_damping = float(link_damping)
+        if contact_breaking is None:       # the Bullet-derived manifold threshold of the toe shape (0.81 mm)
+            from rex_gym_b200.model_tables import contact_breaking_distance
+            contact_breaking = contact_breaking_distance(mark)
+        c.contact_breaking = float(os.environ.get("REXO_BREAKING", contact_breaking))
         for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):
             c.pose_values[k] = float("nan") if v is None else float(v)
         self.cfg = c

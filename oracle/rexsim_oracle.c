@@ -401,8 +401,23 @@ static void aba(const RexoSim* s, const RexoEnv* e, Scratch* k, const real* tau,
         for (int a = 0; a < 3; a++) fg[a] = m->mass[i] * gb[a];
         v3cross(c, fg, ng);
         for (int a = 0; a < 3; a++) { k->pA[i][a] -= ng[a]; k->pA[i][3 + a] -= fg[a]; }
+        /* btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof adds the same damping term to EVERY link
+         * (m_linearDamping = m_angularDamping = 0.04, K1 = K2): I w (k + k|w|), m v (k + k|v|) in the link frame.  Fixed
+         * children are merged here, so the merged body's mass / inertia at its origin stand in for the separate links.
+         * The recorded PyBullet episodes select it: 0.04 on the links lowers the 300-step replay error by 13 %, 0.2 raises it. */
+        if (i > 0 && s->c.link_damping > 0) {
+            const real kl = s->c.link_damping;
+            real* vi = k->v[i];
+            real wn = sqrt(v3dot(vi, vi)), vn = sqrt(v3dot(vi + 3, vi + 3));
+            real Ib[9], Iw[3]; for (int a = 0; a < 9; a++) Ib[a] = m->inertia[i][a];
+            m3v(Ib, vi, Iw);
+            for (int a = 0; a < 3; a++) {
+                k->pA[i][a] += Iw[a] * (kl + kl * wn);
+                k->pA[i][3 + a] += m->mass[i] * vi[3 + a] * (kl + kl * vn);
+            }
+        }
     }
-    /* Bullet base damping: linear/angular damping 0.04 (K1=K2) on the base link only */
+    /* the base link (un-merged root mass / inertia) */
     {
         const real kd = 0.04;
         real* v0 = k->v[0];
@@ -537,6 +552,10 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
     aba(s, e, k, tau, acc);
     for (int a = 0; a < 3; a++) { vel[a] = e->angvel[a] + dt * acc[a]; vel[3 + a] = e->linvel[a] + dt * acc[3 + a]; }
     for (int j = 0; j < m->ndof; j++) vel[6 + j] = e->qd[j] + dt * acc[6 + j];
+    /* btMultiBody::applyDeltaVeeMultiDof clamps every generalised velocity (base included) to +-m_maxCoordinateVelocity
+     * (100, PyBullet's documented maxJointVelocity default) whenever a velocity change is applied */
+    const real vmax = c->max_coordinate_velocity;
+    for (int a = 0; a < nd; a++) { if (vel[a] > vmax) vel[a] = vmax; if (vel[a] < -vmax) vel[a] = -vmax; }
 
     /* 2. constraint rows at the start-of-step configuration */
     int nlim = 0, nn = 0, nf = 0;
@@ -550,15 +569,19 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
             delta_response(s, k, r->J, r->W);
             real den = 0, rel = 0; for (int a = 0; a < nd; a++) { den += r->J[a] * r->W[a]; rel += r->J[a] * vel[a]; }
             r->dinv = 1.0 / den;
-            real erp = (pen > -0.04) ? c->erp_joint : c->erp_contact;
-            r->rhs = (-pen * erp / dt - rel) * r->dinv;
+            /* btMultiBodyJointLimitConstraint::createConstraintRows with m_splitImpulse (Bullet default): a violation deeper than
+             * m_splitImpulsePenetrationThreshold (-0.04) moves the positional term to m_rhsPenetration, which the multibody solver
+             * never applies -- the row then only stops further motion (an overshoot > 0.04 rad is permanent) */
+            r->rhs = (pen > -0.04) ? (-pen * c->erp_joint / dt - rel) * r->dinv : -rel * r->dinv;
             r->lo = 0; r->hi = 1e10; r->applied = 0; r->normal_row = -1;
         }
     }
     e->limit_rows = nlim;
     e->contact_mask = 0;
-    static double g_breaking = -1; if (g_breaking < 0) { const char* ev = getenv("REXO_BREAKING"); g_breaking = ev ? atof(ev) : 0.0005; }
-    const real breaking = g_breaking, slop = 1e-5;
+    /* contact exists while the distance is below the manifold's breaking threshold: btCollisionDispatcher::getNewManifold with
+     * CD_USE_RELATIVE_CONTACT_BREAKING_THRESHOLD = min over the two shapes of getAngularMotionDisc() * gContactBreakingThreshold
+     * (0.02); for the toe link's compound shape that is 0.64 mm (rex_gym_b200/model_tables.py::contact_breaking_distance) */
+    const real breaking = c->contact_breaking, slop = 1e-5;
     for (int sh = 0; sh < m->nshape; sh++) {    /* deepest sample point of each contact group vs ground */
         e->contact_vertex[sh] = -1;
         if (!m->shape_enabled[sh]) continue;
@@ -632,7 +655,7 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
     }
     e->solver_iters = it;
     /* 4. integrate (btMultiBody::stepPositionsMultiDof) */
-    for (int a = 0; a < nd; a++) vel[a] += dV[a];
+    for (int a = 0; a < nd; a++) { vel[a] += dV[a]; if (vel[a] > vmax) vel[a] = vmax; if (vel[a] < -vmax) vel[a] = -vmax; }   /* processDeltaVeeMultiDof2 */
     for (int a = 0; a < 3; a++) { e->angvel[a] = vel[a]; e->linvel[a] = vel[3 + a]; e->pos[a] += dt * vel[3 + a]; }
     for (int j = 0; j < m->ndof; j++) { e->qd[j] = vel[6 + j]; e->q[j] += dt * vel[6 + j]; }
     {   /* exponential-map quaternion update, base body branch of pQuatUpdateFun */
@@ -863,7 +886,8 @@ static double env_reward(RexoSim* s, RexoEnv* e) {
     }
     /* RexGymEnv._reward: rex_gym_env.py:501-542 */
     double cx = -e->pos[0];
-    if (e->backwards) cx = -cx;
+    if (c->backwards == 1) cx = -cx;      /* `self._backwards`, the constructor argument (rex_gym_env.py:269,506): a direction drawn
+                                           * at reset (walk_env.py:133-136 `self.backwards`) does not flip the objective */
     double fwd;
     e->target_position = fabs(e->target_position);
     double tp = e->target_position;

@@ -21,7 +21,8 @@ class RexSimConfig(C.Structure):
         ("normalize", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("seed", C.c_uint64), ("nfields", C.c_int32), ("fields", C.c_void_p),
         ("friction", C.c_float), ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
-        ("toe_npts", C.c_int32), ("toe_margin", C.c_float), ("env_offset", C.c_int32),
+        ("toe_npts", C.c_int32), ("toe_margin", C.c_float),
+        ("contact_breaking", C.c_float), ("link_damping", C.c_float), ("max_coordinate_velocity", C.c_float), ("env_offset", C.c_int32),
         ("gait_clock_scale", C.c_double), ("pose_values", C.c_float * 5),
     ]
 
@@ -38,7 +39,7 @@ AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_cr
 
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
            "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_rebalance", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
-           "rexsim_error_flags", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
+           "rexsim_error_flags", "rexsim_clear_errors", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
 
 _LIB = None
 
@@ -72,6 +73,7 @@ def load():
     L.rexsim_set_state.argtypes = [C.c_void_p] * 3
     L.rexsim_state_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rexsim_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rexsim_clear_errors.argtypes = [C.c_void_p, C.c_void_p]
     L.rexsim_last_command.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.rexsim_launch_count.argtypes = [C.c_void_p]
     L.rexsim_launch_count.restype = C.c_int64

@@ -39,7 +39,7 @@ __device__ __forceinline__ M3 axis_angle(V3 a, float q) {   // Rodrigues, column
 // ABA passes 1 and 2 over the arm: kinematics, bias terms, inward reduction.  Returns the arm's articulated inertia and
 // bias force as seen by the base (to be added to the base sums), fills A.S/U/k/u/cJ.
 static __device__ __noinline__ void arm_inward(const float* __restrict__ AT, const M3& R0, SV v0, Arm& A, const float* tauA,
-                                        AI& IaOut, SV& paOut) {
+                                        AI& IaOut, SV& paOut, float kdamp) {
     AI IAb[ARM_NJ]; SV pAb[ARM_NJ];
     M3 Rp = R0; V3 pp = mk(0.f, 0.f, 0.f); SV vp = v0;
     const float gz = -10.0f;
@@ -56,9 +56,17 @@ static __device__ __noinline__ void arm_inward(const float* __restrict__ AT, con
         SV cJ = crm(v, vj);
         float m = T[15]; V3 cw = pj + mul(Rj, mk(T[16], T[17], T[18]));
         S3 Ib = {T[19], T[20], T[21], T[22], T[23], T[24]};
-        AI I = rigid_inertia(m, cw, rotate_inertia(Rj, Ib));
+        const S3 Iw = rotate_inertia(Rj, Ib);
+        AI I = rigid_inertia(m, cw, Iw);
         SV pA = crf(v, mul(I, v));
         pA.a = pA.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA.l.z -= m * gz;
+        {   // link damping (same term as the legs: rexsim_kernel.cu link_damping)
+            V3 vo = v.l + cross(v.a, pj);
+            float wn = sqrtf(dot(v.a, v.a)), vn = sqrtf(dot(vo, vo));
+            V3 f = (m * fmaf(kdamp, vn, kdamp)) * vo;
+            pA.a = pA.a + fmaf(kdamp, wn, kdamp) * mul(Iw, v.a) + cross(pj, f);
+            pA.l = pA.l + f;
+        }
         IAb[j] = I; pAb[j] = pA;
         st6(A.S[j], S); st6(A.cJ[j], cJ);
         Rp = Rj; pp = pj; vp = v;
@@ -76,14 +84,14 @@ static __device__ __noinline__ void arm_inward(const float* __restrict__ AT, con
     }
 }
 // ABA pass 3: joint accelerations -> unconstrained joint rates A.qs
-static __device__ __noinline__ void arm_outward(Arm& A, SV a0, float dt) {
+static __device__ __noinline__ void arm_outward(Arm& A, SV a0, float dt, float vmax) {
     SV a = a0;
 #pragma unroll 1
     for (int j = 0; j < ARM_NJ; j++) {
         a = a + ld6(A.cJ[j]);
         float qdd = (A.u[j] - sdot(ld6(A.U[j]), a)) * A.k[j];
         a = sfma(qdd, ld6(A.S[j]), a);
-        A.qs[j] = fmaf(dt, qdd, A.qd[j]);
+        A.qs[j] = fminf(fmaxf(fmaf(dt, qdd, A.qd[j]), -vmax), vmax);
     }
 }
 // response of the arm joints to a base velocity change b plus accumulated joint impulses us[] (fixed-base part)

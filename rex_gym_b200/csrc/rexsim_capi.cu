@@ -112,8 +112,8 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     CK(cudaMemset(s->d_snap_i, 0, (size_t)NI * s->nsnap * sizeof(int32_t)));
     CK(cudaMalloc(&s->d_err, (size_t)(N + 1) * sizeof(int32_t)));   /* [N] per-env bits + 1 word: OR of all */
     CK(cudaMemset(s->d_err, 0, (size_t)(N + 1) * sizeof(int32_t)));
-    CK(cudaMalloc(&s->d_cmd, (size_t)12 * N * sizeof(float)));
-    CK(cudaMemset(s->d_cmd, 0, (size_t)12 * N * sizeof(float)));
+    CK(cudaMalloc(&s->d_cmd, (size_t)cfg->num_motors * N * sizeof(float)));
+    CK(cudaMemset(s->d_cmd, 0, (size_t)cfg->num_motors * N * sizeof(float)));
     CK(cudaMalloc(&s->d_perm, (size_t)N * sizeof(int32_t)));
     CK(cudaMalloc(&s->d_cost, (size_t)N * sizeof(int32_t)));
     CK(cudaMemset(s->d_cost, 0, (size_t)N * sizeof(int32_t)));
@@ -202,6 +202,7 @@ int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* strea
     s->launches++;
     if (!zero_copy) CK(cudaMemcpyAsync(h_out, s->d_out, out_err_offset(s), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((char*)h_out + out_err_offset(s), s->d_err + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(s->d_err + N, 0, sizeof(int32_t), st));        // the aggregate is per step on the host path
     CK(cudaStreamSynchronize(st));
     return REXSIM_OK;
 }
@@ -249,6 +250,11 @@ int rexsim_state_buffers(RexSim* s, float** state_f, int32_t** state_i) {
 int rexsim_error_flags(RexSim* s, int32_t** err_flags) {
     if (!s || !err_flags) return fail(REXSIM_ERR_INVALID, "null argument");
     *err_flags = s->d_err;
+    return REXSIM_OK;
+}
+int rexsim_clear_errors(RexSim* s, void* stream) {
+    if (!s) return fail(REXSIM_ERR_INVALID, "null handle");
+    CK(cudaMemsetAsync(s->d_err + s->P.N, 0, sizeof(int32_t), (cudaStream_t)stream));
     return REXSIM_OK;
 }
 int rexsim_last_command(RexSim* s, float** cmd) {

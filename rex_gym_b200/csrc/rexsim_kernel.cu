@@ -234,6 +234,19 @@ __device__ __forceinline__ float motor_torque(float cmd, float q, float qd, floa
     return copysignf(t, cur) * (cur != 0.f ? 1.f : 0.f);
 }
 
+// btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof adds the damping term of the base to EVERY link too
+// (m_linearDamping = m_angularDamping = 0.04, K1 = K2): torque I w (k + k|w|) about the link origin and force
+// m v_o (k + k|v_o|) at it, v_o = velocity of the link origin.  Expressed about the common-frame origin (the base position).
+__device__ __forceinline__ void link_damping(float k, float m, const S3& Iw, V3 p, const SV& v, SV& pA) {
+    V3 vo = v.l + cross(v.a, p);
+    float wn = sqrtf(dot(v.a, v.a)), vn = sqrtf(dot(vo, vo));
+    V3 f = (m * fmaf(k, vn, k)) * vo;
+    V3 n = fmaf(k, wn, k) * mul(Iw, v.a);
+    pA.a = pA.a + n + cross(p, f);
+    pA.l = pA.l + f;
+}
+__device__ __forceinline__ float clampv(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
+
 // -------------------------------------------------------------------------------------------------
 // one pybullet.stepSimulation for the 4 lanes of an env (call site rex_gym/model/rex.py:161)
 // -------------------------------------------------------------------------------------------------
@@ -267,23 +280,29 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     {
         float m = LB[3]; V3 cw = p1 + mul(R1, mk(LB[4], LB[5], LB[6]));
         S3 Ib = {LB[8], LB[9], LB[10], LB[11], LB[12], LB[13]};
-        IA1 = rigid_inertia(m, cw, (LB[15] != 0.f ? rotate_inertia_diag(R1, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R1, Ib)));
+        const S3 Iw = (LB[15] != 0.f ? rotate_inertia_diag(R1, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R1, Ib));
+        IA1 = rigid_inertia(m, cw, Iw);
         pA1 = crf(v1, mul(IA1, v1));
         pA1.a = pA1.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA1.l.z -= m * gz;
+        link_damping(P.cfg.link_damping, m, Iw, p1, v1, pA1);
     }
     {
         float m = LB[16 + 3]; V3 cw = p2 + mul(R2, mk(LB[16 + 4], LB[16 + 5], LB[16 + 6]));
         S3 Ib = {LB[16 + 8], LB[16 + 9], LB[16 + 10], LB[16 + 11], LB[16 + 12], LB[16 + 13]};
-        IA2 = rigid_inertia(m, cw, (LB[16 + 15] != 0.f ? rotate_inertia_diag(R2, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R2, Ib)));
+        const S3 Iw = (LB[16 + 15] != 0.f ? rotate_inertia_diag(R2, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R2, Ib));
+        IA2 = rigid_inertia(m, cw, Iw);
         pA2 = crf(v2, mul(IA2, v2));
         pA2.a = pA2.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA2.l.z -= m * gz;
+        link_damping(P.cfg.link_damping, m, Iw, p2, v2, pA2);
     }
     {
         float m = LB[32 + 3]; V3 cw = p3 + mul(R3, mk(LB[32 + 4], LB[32 + 5], LB[32 + 6]));
         S3 Ib = {LB[32 + 8], LB[32 + 9], LB[32 + 10], LB[32 + 11], LB[32 + 12], LB[32 + 13]};
-        IA3 = rigid_inertia(m, cw, (LB[32 + 15] != 0.f ? rotate_inertia_diag(R3, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R3, Ib)));
+        const S3 Iw = (LB[32 + 15] != 0.f ? rotate_inertia_diag(R3, Ib.xx, Ib.yy, Ib.zz) : rotate_inertia(R3, Ib));
+        IA3 = rigid_inertia(m, cw, Iw);
         pA3 = crf(v3, mul(IA3, v3));
         pA3.a = pA3.a - mk(cw.y * m * gz, -cw.x * m * gz, 0.f); pA3.l.z -= m * gz;
+        link_damping(P.cfg.link_damping, m, Iw, p3, v3, pA3);
     }
     // ---- ABA inward pass over the own leg ------------------------------------------------------------
     SV U3 = mul(IA3, S3v); float k3 = 1.0f / sdot(S3v, U3); float u3 = tau[2] - sdot(S3v, pA3);
@@ -299,7 +318,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     pA1 = sfma(u1 * k1, U1, pA1 + mul(IA1, cJ1));
     if (ARM && leg == 0) {   // the arm is a fifth limb of lane 0: fold its articulated inertia into this lane's sum
         AI Ia; SV pa; SV vb; vb.a = L.w; vb.l = L.vl;
-        arm_inward(sm + REXSIM_MT_ARM, R0, vb, AR, tauA, Ia, pa);
+        arm_inward(sm + REXSIM_MT_ARM, R0, vb, AR, tauA, Ia, pa, P.cfg.link_damping);
         add(IA1, Ia); pA1 = pA1 + pa;
     }
     // ---- base: reduce the 4 legs, add the base body, invert ------------------------------------------
@@ -336,7 +355,12 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     // unconstrained velocities (btMultiBodyDynamicsWorld::solveConstraints: v += a*dt)
     SV vs; vs.a = fma3(dt, a0.a, L.w); vs.l = fma3(dt, a0.l + cross(L.w, L.vl), L.vl);
     float qs1 = fmaf(dt, qdd1, L.qd[0]), qs2 = fmaf(dt, qdd2, L.qd[1]), qs3 = fmaf(dt, qdd3, L.qd[2]);
-    if (ARM && leg == 0) arm_outward(AR, a0, dt);
+    // btMultiBody::applyDeltaVeeMultiDof clamps all 6+n generalised velocities to +-m_maxCoordinateVelocity (100)
+    const float vmax = P.cfg.max_coordinate_velocity;
+    vs.a = mk(clampv(vs.a.x, vmax), clampv(vs.a.y, vmax), clampv(vs.a.z, vmax));
+    vs.l = mk(clampv(vs.l.x, vmax), clampv(vs.l.y, vmax), clampv(vs.l.z, vmax));
+    qs1 = clampv(qs1, vmax); qs2 = clampv(qs2, vmax); qs3 = clampv(qs3, vmax);
+    if (ARM && leg == 0) arm_outward(AR, a0, dt, vmax);
 
     // ---- contact candidates: ONE contact per group = its deepest sample point (same groups/order as the oracle) ----
     //   foot group  (own lane): foot box corners, then the toe hull (exact prism support, toe_margin = 0)
@@ -479,9 +503,12 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             if (od < bestB || (od == bestB && oj < jb)) { bestB = od; jb = oj; rcB = orc; nrmB = onr; }
         }
     }
-    const bool active = best <= 0.0005f;
-    const bool activeU = bestU <= 0.0005f;
-    const bool activeB = (leg == 0) && (bestB <= 0.0005f);
+    // contact while the distance is below the manifold's breaking threshold (btCollisionDispatcher::getNewManifold, relative
+    // threshold: getAngularMotionDisc() * 0.02 of the toe link's shape = 0.64 mm; model_tables.contact_breaking_distance)
+    const float brk = P.cfg.contact_breaking;
+    const bool active = best <= brk;
+    const bool activeU = bestU <= brk;
+    const bool activeB = (leg == 0) && (bestB <= brk);
     // joint limits (btMultiBodyJointLimitConstraint: a row only while the limit is violated); one row per leg is modelled
     int limJ = -1; float limSg = 0.f, limPen = 0.f;
     {
@@ -691,8 +718,9 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         if (limJ >= 0) {
             SV z; z.a = mk(0, 0, 0); z.l = mk(0, 0, 0);
             float relv = setup_row(0, z, limJ == 0 ? limSg : 0.f, limJ == 1 ? limSg : 0.f, limJ == 2 ? limSg : 0.f);
-            float erp = (limPen > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
-            rhs_[0] = (-limPen * erp * inv_dt - relv) * dinv_[0];
+            // btMultiBodyJointLimitConstraint with m_splitImpulse: beyond the -0.04 threshold the positional term goes to
+            // m_rhsPenetration, which the multibody solver never applies (the row only stops further motion)
+            rhs_[0] = (limPen > -0.04f) ? (-limPen * P.cfg.erp_joint * inv_dt - relv) * dinv_[0] : -relv * dinv_[0];
         }
         if (activeB) setup_contact(1, rcB, nrmB, 0, bestB);
         if (activeU) setup_contact(4, rcU, nrmU, kU, bestU);
@@ -713,8 +741,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 float dn = -sdot(gg, bb) + armSg[j] * eeA_[j][j];
                 denA_[j] = dn; dinvA_[j] = 1.0f / dn;
                 float relv = armSg[j] * AR.qs[j];
-                float erp = (armPen[j] > -0.04f) ? P.cfg.erp_joint : P.cfg.erp_contact;
-                rhsA_[j] = (-armPen[j] * erp * inv_dt - relv) * dinvA_[j];
+                rhsA_[j] = (armPen[j] > -0.04f) ? (-armPen[j] * P.cfg.erp_joint * inv_dt - relv) * dinvA_[j] : -relv * dinvA_[j];
             }
         }
         SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);
@@ -798,12 +825,14 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     }
     // ---- integrate (btMultiBody::stepPositionsMultiDof) --------------------------------------------------
     L.w = vs.a + dv0.a; L.vl = vs.l + dv0.l;
-    L.qd[0] = qs1 + dq1; L.qd[1] = qs2 + dq2; L.qd[2] = qs3 + dq3;
+    L.w = mk(clampv(L.w.x, vmax), clampv(L.w.y, vmax), clampv(L.w.z, vmax));          // processDeltaVeeMultiDof2 -> applyDeltaVee
+    L.vl = mk(clampv(L.vl.x, vmax), clampv(L.vl.y, vmax), clampv(L.vl.z, vmax));
+    L.qd[0] = clampv(qs1 + dq1, vmax); L.qd[1] = clampv(qs2 + dq2, vmax); L.qd[2] = clampv(qs3 + dq3, vmax);
     L.pos = fma3(dt, L.vl, L.pos);
     L.q[0] = fmaf(dt, L.qd[0], L.q[0]); L.q[1] = fmaf(dt, L.qd[1], L.q[1]); L.q[2] = fmaf(dt, L.qd[2], L.q[2]);
     if (ARM && leg == 0) {
 #pragma unroll
-        for (int j = 0; j < ARM_NJ; j++) { AR.qd[j] = AR.qs[j] + dqA[j]; AR.q[j] = fmaf(dt, AR.qd[j], AR.q[j]); }
+        for (int j = 0; j < ARM_NJ; j++) { AR.qd[j] = clampv(AR.qs[j] + dqA[j], vmax); AR.q[j] = fmaf(dt, AR.qd[j], AR.q[j]); }
     }
     {
         float fa = sqrtf(dot(L.w, L.w));
@@ -1196,7 +1225,9 @@ __device__ __forceinline__ void store_arm(float* sf, int32_t* si, int N, int env
 
 // reset one env from the settled snapshot + task draws (BatchEnv.reset -> <task>.reset; rex.py:255-324)
 template <bool ARM>
-__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field, Arm& AR) {
+// `valid` is false on the padding lanes that replicate the last env to keep warps whole: they compute, but never write
+// (a replica that re-read the counter after the real lane's write would otherwise bump it twice)
+__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field, Arm& AR, bool valid) {
     const RexSimConfig& c = P.cfg;
     const int N = P.N;
     uint32_t rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env] + 1u;
@@ -1249,7 +1280,7 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
         }
         K.flags = (K.flags & ~(7 << FL_POSE_SHIFT)) | (pose << FL_POSE_SHIFT);
     }
-    if (leg == 0) {
+    if (valid && leg == 0) {
         P.si[I_RESETCNT * (size_t)N + env] = (int32_t)rc;
         P.si[I_FIELD * (size_t)N + env] = field;
         P.sf[F_KP * (size_t)N + env] = kp; P.sf[F_KD * (size_t)N + env] = kd;
@@ -1349,6 +1380,10 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     if (valid) {
 #pragma unroll
         for (int j = 0; j < 3; j++) P.cmd_out[(size_t)(3 * leg + j) * N + env] = cmd[j];
+        if (ARM && leg == 0) {            // the arm holds ARM_POSES['rest'] (rex_gym_env.py:363-367): info['action'] has all 18
+#pragma unroll
+            for (int j = 0; j < ARM_NJ; j++) P.cmd_out[(size_t)(12 + j) * N + env] = c_arm_rest[j];
+        }
     }
     // Rex.Step (rex.py:158-163)
     for (int r = 0; r < c.action_repeat; r++) {
@@ -1368,7 +1403,9 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
         reward = pr;
     } else {
         float cx = -L.pos.x;
-        if (K.flags & FL_BACKWARDS) cx = -cx;
+        // the reference flips on the CONSTRUCTOR argument only (rex_gym_env.py:269,506 `self._backwards`): a direction drawn
+        // at reset (walk_env.py:133-136, `self.backwards`) leaves the forward objective unflipped -- restated as is
+        if (c.backwards == 1) cx = -cx;
         K.target = fabsf(K.target);
         float tp = K.target, fwd;
         if (cx > tp + 0.15f) fwd = tp - cx;
@@ -1408,11 +1445,14 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
         if (P.cost) P.cost[env] = L.cost;
         P.reward[env] = reward;
         P.done[env] = done ? 1 : 0;
-        if (err) { P.err[env] |= err; atomicOr(&P.err[N], err); }
+        // per-env word = the error bits of this env's most recent step (ConvertTo32Bit raises for the offending step only,
+        // wrappers.py:522-523,542-543); the aggregate word [N] accumulates until the host reads and clears it
+        P.err[env] = err;
+        if (err) atomicOr(&P.err[N], err);
     }
     // ---- auto reset: done envs restart from the settled snapshot; obs = first observation of the new episode --
     if (c.auto_reset && done) {
-        reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR);
+        reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, valid);
         if (valid) write_obs<TASK>(P, env, leg, L, obs_row);
     }
     store_lane(P.sf, P.si, N, env, leg, L, K, valid);
@@ -1431,12 +1471,18 @@ __global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_o
     const bool valid = j < k;
     if (!valid) j = k - 1;
     int env = P.reset_idx ? P.reset_idx[j] : j;
+    // an index outside [0, N) never touches state: the lane is parked on env 0 with its stores masked, the aggregate
+    // error word gets REXSIM_FLAG_BAD_INDEX (the Python mirror raises IndexError like BatchEnv.reset would)
+    const bool inrange = env >= 0 && env < P.N;
+    if (!inrange) { if (valid && leg == 0) atomicOr(&P.err[P.N], REXSIM_FLAG_BAD_INDEX); env = 0; }
+    const bool wr = valid && inrange;
     const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
     Lane L; Task K; Arm AR; float kp, kd; int field;
-    reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR);
-    if (valid && obs_out) write_obs<TASK>(P, env, leg, L, obs_out + (size_t)j * O);
-    store_lane(P.sf, P.si, P.N, env, leg, L, K, valid);
-    if (ARM && valid && leg == 0) store_arm(P.sf, P.si, P.N, env, AR);
+    reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, wr);
+    if (wr && obs_out) write_obs<TASK>(P, env, leg, L, obs_out + (size_t)j * O);
+    if (wr && leg == 0) P.err[env] = 0;
+    store_lane(P.sf, P.si, P.N, env, leg, L, K, wr);
+    if (ARM && wr && leg == 0) store_arm(P.sf, P.si, P.N, env, AR);
 }
 
 // -------------------------------------------------------------------------------------------------

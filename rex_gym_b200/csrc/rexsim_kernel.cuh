@@ -50,7 +50,7 @@ struct Params {
     const int32_t* __restrict__ snap_i;// [nsnap][NI]
     const float* __restrict__ field_zoff; // [nfields]
     int32_t* __restrict__ err;         // [N]
-    float* __restrict__ cmd_out;       // [12][N]
+    float* __restrict__ cmd_out;       // [num_motors][N]
     const float* __restrict__ actions; // [N][A]
     float* __restrict__ obs;           // [N][O]
     float* __restrict__ reward;        // [N]

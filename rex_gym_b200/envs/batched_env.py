@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from .. import _capi
-from ..model_tables import pack_model_tables, TOE_MARGIN
+from ..model_tables import (pack_model_tables, contact_breaking_distance, TOE_MARGIN, LINK_DAMPING,
+                            MAX_COORDINATE_VELOCITY)
 from ..terrain import make_random_fields
 from .spaces import Box
 
@@ -27,7 +28,7 @@ ACTION_BOUND = {("walk", "ik"): 0.4, ("walk", "ol"): 0.01, ("gallop", "ik"): 0.4
                 ("turn", "ik"): 0.01, ("turn", "ol"): 0.01, ("standup", "ol"): 0.1, ("standup", "ik"): 0.1,
                 ("poses", "ik"): 0.1, ("poses", "ol"): 0.1}
 
-ERR_NONFINITE, ERR_JOINT_LIMIT, ERR_BODY_CONTACT = 1, 2, 4
+ERR_NONFINITE, ERR_JOINT_LIMIT, ERR_BODY_CONTACT, ERR_TILE_MISS, ERR_BAD_INDEX = 1, 2, 4, 8, 16
 
 
 class _DevArray(object):
@@ -39,21 +40,27 @@ class _DevArray(object):
 
 
 class _Info(object):
-    """Lazy stand-in for BatchEnv's `tuple(infos)`: info[i] == {'action': motor command of env i}."""
+    """Stand-in for BatchEnv's `tuple(infos)`: info[i] == {'action': motor command of env i} of THE STEP THAT RETURNED IT
+    (rex_gym_env.py:414).  The command block lives on the device and is overwritten by the next step, so the host copy is taken
+    on first access; an access after the batch has stepped again raises instead of handing out the later step's commands."""
 
     def __init__(self, env):
-        self._env, self._cmd = env, None
+        self._env, self._cmd, self._at = env, None, env._nsteps
 
     def __len__(self):
         return len(self._env)
 
-    def __getitem__(self, i):
+    def materialize(self):
+        """Take the host copy now (one device sync + D2H copy of [N][num_motors] floats)."""
         if self._cmd is None:
-            c = self._env.last_command().t().contiguous().cpu().numpy()
-            if self._env.num_motors == 18:          # the arm holds ARM_POSES['rest'] (rex_gym_env.py:363-367)
-                c = np.concatenate([c, np.tile(np.array([-1.6, -1.6, 0., 0., 1.6, 0.], np.float32), (c.shape[0], 1))], axis=1)
-            self._cmd = c
-        return {"action": self._cmd[i]}
+            if self._env._nsteps != self._at:
+                raise RuntimeError("info of step %d read after the batch advanced to step %d: call info.materialize() (or read "
+                                   "info[i]) before the next step()" % (self._at, self._env._nsteps))
+            self._cmd = self._env.last_command().t().contiguous().cpu().numpy()
+        return self
+
+    def __getitem__(self, i):
+        return {"action": self.materialize()._cmd[i]}
 
 
 class _EnvView(object):
@@ -96,6 +103,7 @@ class BatchedRexEnv(object):
         if not torch.cuda.is_available():
             raise RuntimeError("rex_gym_b200 needs a CUDA device: there is no CPU fallback")
         self._L = _capi.load()
+        self._debug = bool(debug)
         self.task, self.signal_type, self.terrain_type, self.mark = task, signal_type, terrain_type, mark
         self.device = torch.device(device)
         self.num_envs = int(num_envs)
@@ -115,7 +123,8 @@ class BatchedRexEnv(object):
         c.motor_kp, c.motor_kd = motor_kp, motor_kd
         c.kp_lo, c.kp_hi = motor_kp_range or (motor_kp, motor_kp)
         c.kd_lo, c.kd_hi = motor_kd_range or (motor_kd, motor_kd)
-        c.target_position = float("nan") if target_position is None else target_position
+        # `if not self._target_position` (walk_env.py:144, gallop_env.py:150): None AND 0 mean "draw one per reset"
+        c.target_position = float("nan") if not target_position else target_position
         c.backwards = -1 if backwards is None else int(bool(backwards))
         c.target_orient = float("nan") if target_orient is None else target_orient
         c.init_orient = float("nan") if init_orient is None else init_orient
@@ -136,6 +145,8 @@ class BatchedRexEnv(object):
                 c.friction = 0.5 * 1.0          # x plane.urdf lateral_friction 1
             c.residual_threshold, c.erp_contact, c.erp_joint = 1e-7, 0.08, 0.2
             c.toe_npts, c.toe_margin = toe_npts, TOE_MARGIN
+            c.contact_breaking = contact_breaking_distance(mark)
+            c.link_damping, c.max_coordinate_velocity = LINK_DAMPING, MAX_COORDINATE_VELOCITY
             c.env_offset = int(env_offset)
             self._cfg = c
             h = C.c_void_p()
@@ -168,7 +179,7 @@ class BatchedRexEnv(object):
         _capi.check(self._L.rexsim_error_flags(self._h, C.byref(p)))
         self._err = torch.as_tensor(_DevArray(p.value, (N + 1,), "<i4", self), device=dev)
         _capi.check(self._L.rexsim_last_command(self._h, C.byref(p)))
-        self._cmd = torch.as_tensor(_DevArray(p.value, (12, N), "<f4", self), device=dev)
+        self._cmd = torch.as_tensor(_DevArray(p.value, (self.num_motors, N), "<f4", self), device=dev)
         nf, ni = C.c_int32(), C.c_int32()
         _capi.check(self._L.rexsim_state_words(C.byref(c), C.byref(nf), C.byref(ni)))
         pf, pi = C.c_void_p(), C.c_void_p()
@@ -245,7 +256,7 @@ class BatchedRexEnv(object):
         if rc:
             _capi.check(rc)
         self._maybe_rebalance()
-        if self._h_err[0] & ERR_NONFINITE:
+        if self._h_err[0] & ERR_NONFINITE:        # the aggregate word is per step on this path (rexsim_step_host clears it)
             raise ValueError("Infinite observation encountered.")          # ConvertTo32Bit wrappers.py:522-523,542-543
         return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), _Info(self)
 
@@ -263,7 +274,11 @@ class BatchedRexEnv(object):
                 k, idx_ptr = self.num_envs, None
             else:
                 if isinstance(indices, torch.Tensor):
+                    # device indices are not inspected on the host: the kernel skips any index outside [0, N) and raises
+                    # REXSIM_FLAG_BAD_INDEX in the aggregate error word (check_errors() -> IndexError); debug=True checks here
                     idx = indices.to(device=self.device, dtype=torch.int32).contiguous()
+                    if self._debug and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.num_envs):
+                        raise IndexError("reset index out of range")
                 else:
                     ia = np.asarray(indices, dtype=np.int64).reshape(-1)
                     if ia.size and (ia.min() < 0 or ia.max() >= self.num_envs):
@@ -312,16 +327,24 @@ class BatchedRexEnv(object):
             torch.cuda.current_stream(self.device).synchronize()
 
     def last_command(self):
-        """[12, N] motor commands of the last step (info['action'], rex_gym_env.py:414)."""
+        """[num_motors, N] motor commands of the last step (info['action'], rex_gym_env.py:414)."""
         return self._cmd
 
     def error_flags(self):
         return self._err[:self.num_envs]
 
     def check_errors(self):
+        """Read AND clear the aggregate error word (every bit raised since the last call; one device sync).  Raises like the
+        reference would have for the offending step: ValueError for a non-finite observation (ConvertTo32Bit), IndexError for a
+        reset index outside the batch; returns the remaining (informational) bits."""
         e = int(self._err[self.num_envs].item())
+        if e:
+            with torch.cuda.device(self.device):
+                _capi.check(self._L.rexsim_clear_errors(self._h, self._stream()))
         if e & ERR_NONFINITE:
             raise ValueError("Infinite observation encountered.")
+        if e & ERR_BAD_INDEX:
+            raise IndexError("reset index out of range")
         return e
 
     def state_dict(self):

@@ -15,6 +15,7 @@ def fresh(no_damping=False, dt=None, **kw):
     s = OracleSim(1, "walk", settle=False, target_position=2.0, backwards=False, **kw)
     if no_damping or dt:
         if no_damping:
+            s.cfg.link_damping = 0.0
             s.model.root_mass = 0.0
             for a in range(3):
                 s.model.root_inertia[a] = 0.0

@@ -12,7 +12,7 @@ walk_env.py:292-315, turn_env.py:271-311) -- no wall-clock gait phase -- so repl
 initial observation is a like-for-like test of pybullet.stepSimulation + the motor model, the part of the hot path whose
 parity could not be pinned any other way (pybullet is not installable here).
 
-Output: tests/golden/pybullet_memory_golden.npz  (first STEPS control steps of EPISODES episodes per task; float32 as stored).
+Output: tests/golden/pybullet_memory_golden.npz  (first STEPS[task] control steps of all 25 episodes per task; float32 as stored).
   <task>_<signal>_action [E][K][A]    policy output, before ClipAction / denormalisation (wrappers.py:218-265)
   <task>_<signal>_observ [E][K+1][O]  RangeNormalize'd observation BEFORE each step (row 0 = reset observation)
   <task>_<signal>_reward [E][K]
@@ -29,7 +29,11 @@ from rex_gym_b200.agents import tf_checkpoint as tfc  # noqa: E402
 REF = "/root/reference/rex_gym/policies"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "pybullet_memory_golden.npz")
 TASKS = [("gallop", "ol"), ("walk", "ol"), ("turn", "ol"), ("standup", "ol")]
-EPISODES, STEPS = 12, 160
+EPISODES = 25                      # update_every = 25: every episode the memory holds
+# control steps kept per episode: gallop 600 (no recorded episode reaches its goal before step 511; the target, hence the brake
+# phase, is a per-episode random draw that was not recorded), walk 600 (the first goal is reached after step 400), standup: all
+# 400, turn 160 (rows beyond `length` belong to older episodes)
+STEPS = {"gallop": 600, "walk": 600, "turn": 160, "standup": 400}
 
 
 def main():
@@ -39,9 +43,10 @@ def main():
         v = tfc.load_variables(prefix, ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
         ob, ac, rw = v["memory/Variable_1"], v["memory/Variable_2"], v["memory/Variable_5"]
         name = "%s_%s" % (task, sig)
-        out[name + "_action"] = ac[:EPISODES, :STEPS].astype(np.float32)
-        out[name + "_observ"] = ob[:EPISODES, :STEPS + 1].astype(np.float32)
-        out[name + "_reward"] = rw[:EPISODES, :STEPS].astype(np.float32)
+        n = STEPS[task]
+        out[name + "_action"] = ac[:EPISODES, :n].astype(np.float32)
+        out[name + "_observ"] = ob[:EPISODES, :n + 1].astype(np.float32)
+        out[name + "_reward"] = rw[:EPISODES, :n].astype(np.float32)
         print(name, os.path.basename(prefix), "memory", ob.shape, "->", out[name + "_observ"].shape)
     # walk-ik: NOT replayable step by step (the gait phase ran on the wall clock, gait_planner.py:108-110), kept for the
     # statistical test of the wall-clock emulation (gait_clock_scale): 300 steps of 6 episodes
