@@ -49,7 +49,9 @@ class RexoConfig(C.Structure):
         ("residual_threshold", C.c_double), ("erp_contact", C.c_double), ("erp_joint", C.c_double),
         ("settle_on_reset", C.c_int32), ("env_offset", C.c_int32), ("gait_clock_scale", C.c_double),
         ("link_damping", C.c_double), ("contact_breaking", C.c_double),
-        ("max_coordinate_velocity", C.c_double), ("pose_values", C.c_double * 5),
+        ("max_coordinate_velocity", C.c_double),
+        ("control_latency", C.c_double), ("pd_latency", C.c_double), ("noise_stdev", C.c_double * 5),
+        ("pose_values", C.c_double * 5),
     ]
 
 
@@ -100,6 +102,11 @@ def lib(f32=False):
         L.rexo_physics_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rexo_rand_u32.restype = C.c_uint32
         L.rexo_rand_u32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.rexo_sensor_clear.argtypes = [C.c_void_p, C.c_int]
+        L.rexo_sensor_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.rexo_sensor_delayed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.rexo_noise.restype = C.c_double
+        L.rexo_noise.argtypes = [C.c_uint64] + [C.c_uint32] * 5
         L.rexo_mass_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rexo_aba.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.rexo_kinetic_momentum.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
@@ -202,7 +209,7 @@ class OracleSim:
                  solver_iterations=None, residual_threshold=1e-7, env_offset=0,
                  base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, terrain_full_toe=False,
                  gait_clock_scale=1.0, max_coordinate_velocity=100.0,
-                 link_damping=0.04, contact_breaking=None):
+                 link_damping=0.04, contact_breaking=None, control_latency=0.0, pd_latency=0.0, observation_noise_stdev=None):
         self.L = lib(f32)
         self.model, self.model_json = load_model(mark, toes_only=toes_only, terrain_full_toe=terrain_full_toe)
         c = RexoConfig()
@@ -240,6 +247,9 @@ class OracleSim:
         c.gait_clock_scale = float(gait_clock_scale)
         c.max_coordinate_velocity = float(max_coordinate_velocity)
         c.link_damping = float(link_damping)
+        c.control_latency, c.pd_latency = float(control_latency), float(pd_latency)
+        for k, v in enumerate(observation_noise_stdev or (0.0,) * 5):      # SENSOR_NOISE_STDDEV rex.py:22
+            c.noise_stdev[k] = float(v)
         if contact_breaking is None:       # the Bullet-derived manifold threshold of the toe shape (0.81 mm)
             from rex_gym_b200.model_tables import contact_breaking_distance
             contact_breaking = contact_breaking_distance(mark)

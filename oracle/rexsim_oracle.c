@@ -151,6 +151,7 @@ static void solve6(const real* A, const real* b, real* x) {
 /* ------------------------------------------------------------------------------------------- */
 /* simulator object                                                                             */
 /* ------------------------------------------------------------------------------------------- */
+struct Hist;
 struct RexoSim {
     RexoModel m;
     RexoConfig c;
@@ -161,7 +162,12 @@ struct RexoSim {
     double init_pose[REXO_MAXDOF];   /* task init pose incl. arm rest */
     double stand_pose[REXO_MAXDOF];  /* Rex.initial_pose = INIT_POSES['stand'] (+arm rest) */
     double field_zoff[256];          /* (hmin+hmax)/2 per field */
+    /* sensor history: one ring per env, then one per reset snapshot; ctrl = the control observation of the last ReceiveObservation */
+    struct Hist* hist;
+    double (*ctrl)[REXO_OBSW];
+    int sensor_on;                    /* any latency or noise configured */
 };
+typedef struct Hist { int len, head; double buf[REXO_HIST][REXO_OBSW]; } Hist;
 
 /* per-sub-step scratch (kinematics + ABA caches) */
 typedef struct {
@@ -678,14 +684,86 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* sensor history, latency and noise: rex_gym/model/rex.py:717-769                               */
+/* ------------------------------------------------------------------------------------------- */
+static Hist* hist_of(RexoSim* s, const RexoEnv* e) {
+    if (e >= s->env && e < s->env + s->c.num_envs) return &s->hist[e - s->env];
+    return &s->hist[s->c.num_envs + (e - s->snapshot)];
+}
+static double* ctrl_of(RexoSim* s, const RexoEnv* e) {
+    if (e >= s->env && e < s->env + s->c.num_envs) return s->ctrl[e - s->env];
+    return s->ctrl[s->c.num_envs + (e - s->snapshot)];
+}
+static void hist_push(Hist* h, const double* obs, int w) {        /* deque.appendleft, maxlen 100 (rex.py:122,733) */
+    h->head = (h->head + 1) % REXO_HIST;
+    memcpy(h->buf[h->head], obs, sizeof(double) * w);
+    if (h->len < REXO_HIST) h->len++;
+}
+static const double* hist_at(const Hist* h, int k) { return h->buf[(h->head - k + 2 * REXO_HIST) % REXO_HIST]; }   /* history[k] */
+static void hist_delayed(const Hist* h, double latency, double dt, int w, double* out) {   /* _GetDelayedObservation rex.py:735-753 */
+    if (latency <= 0 || h->len == 1) { memcpy(out, hist_at(h, 0), sizeof(double) * w); return; }
+    int n = (int)(latency / dt);
+    if (n + 1 >= h->len) { memcpy(out, hist_at(h, h->len - 1), sizeof(double) * w); return; }
+    double remaining = latency - n * dt;
+    double alpha = remaining / dt;
+    const double* a = hist_at(h, n); const double* b = hist_at(h, n + 1);
+    for (int i = 0; i < w; i++) out[i] = (1.0 - alpha) * a[i] + alpha * b[i];
+}
+static void true_observation(const RexoSim* s, const RexoEnv* e, double* o) {     /* GetTrueObservation rex.py:717-724 */
+    const RexoModel* m = &s->m; int n = m->nmotor;
+    for (int i = 0; i < n; i++) { o[i] = e->q[m->motor_dof[i]]; o[n + i] = e->qd[m->motor_dof[i]]; o[2 * n + i] = e->tau_obs[i]; }
+    for (int a = 0; a < 4; a++) o[3 * n + a] = e->quat[a];
+    for (int a = 0; a < 3; a++) o[3 * n + 4 + a] = e->angvel[a];
+}
+static void receive_observation(RexoSim* s, RexoEnv* e) {                          /* ReceiveObservation rex.py:726-733 */
+    if (!s->sensor_on) return;
+    double o[REXO_OBSW]; true_observation(s, e, o);
+    Hist* h = hist_of(s, e);
+    hist_push(h, o, 3 * s->m.nmotor + 7);
+    hist_delayed(h, s->c.control_latency, s->c.sim_dt, 3 * s->m.nmotor + 7, ctrl_of(s, e));
+}
+/* Counter-based N(0,1) (Box-Muller on two draws of the reset generator) replacing the unseeded np.random.normal of
+ * _AddSensorNoise (rex.py:763-769).  Keyed on (seed, global env, reset count, control step since reset, call site, component);
+ * sites: 0 observation rpy, 1 observation rpy rate, 2 observation motor angles, 3 reward orientation, 4 reward torques,
+ * 5 reward velocities, 6 termination orientation, 7 turn goal-check orientation */
+double rexo_noise(uint64_t seed, uint32_t env, uint32_t reset_count, uint32_t step, uint32_t site, uint32_t comp) {
+    uint32_t slot = 1024u + (((step * 8u + site) * 32u + comp) << 1);
+    double u1 = ((double)(rexo_rand_u32(seed, env, reset_count, slot) >> 8) + 1.0) * (1.0 / 16777216.0);
+    double u2 = (double)(rexo_rand_u32(seed, env, reset_count, slot + 1u) >> 8) * (1.0 / 16777216.0);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * PI * u2);
+}
+static double noise(const RexoSim* s, const RexoEnv* e, int group, uint32_t site, uint32_t comp) {
+    double sd = s->c.noise_stdev[group];
+    if (sd <= 0) return 0.0;
+    uint32_t genv = (uint32_t)(e - s->env) + (uint32_t)s->c.env_offset;
+    return sd * rexo_noise(s->c.seed, genv, e->reset_count, (uint32_t)e->env_step_counter, site, comp);
+}
+/* Rex.GetBaseRollPitchYaw (rex.py:429-442): Euler angles of the DELAYED orientation + noise; GetBaseOrientation (:530-537) turns
+ * them back into a quaternion.  With the sensor model off this is the true orientation (no round trip: bit-stable with round 1). */
+static void sensed_quat(RexoSim* s, RexoEnv* e, uint32_t site, real* q4) {
+    if (!s->sensor_on) { for (int a = 0; a < 4; a++) q4[a] = e->quat[a]; return; }
+    const double* c = ctrl_of(s, e) + 3 * s->m.nmotor;
+    real d4[4] = {c[0], c[1], c[2], c[3]}, rpy[3];
+    quat_to_euler(d4, rpy);
+    for (int a = 0; a < 3; a++) rpy[a] += noise(s, e, 3, site, a);
+    euler_to_quat(rpy, q4);
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* Rex.ApplyAction + stepSimulation + ReceiveObservation: rex_gym/model/rex.py:158-163,568-641   */
 /* ------------------------------------------------------------------------------------------- */
 static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {
     const RexoModel* m = &s->m;
     int n = m->nmotor;
     double q[REXO_MAXDOF], qd[REXO_MAXDOF], kp[REXO_MAXDOF], kd[REXO_MAXDOF], ta[REXO_MAXDOF], to[REXO_MAXDOF];
-    for (int i = 0; i < n; i++) { q[i] = e->q[m->motor_dof[i]]; qd[i] = e->qd[m->motor_dof[i]]; kp[i] = e->kp; kd[i] = e->kd; }
-    rexo_motor_torque(n, cmd, q, qd, qd, kp, kd, ta, to);        /* rex.py:596-600 (zero pd latency) */
+    double qd_true[REXO_MAXDOF];
+    for (int i = 0; i < n; i++) { q[i] = e->q[m->motor_dof[i]]; qd[i] = e->qd[m->motor_dof[i]]; qd_true[i] = qd[i]; kp[i] = e->kp; kd[i] = e->kd; }
+    if (s->sensor_on && s->c.pd_latency > 0 && hist_of(s, e)->len > 0) {       /* _GetPDObservation rex.py:755-759 */
+        double pdo[REXO_OBSW];
+        hist_delayed(hist_of(s, e), s->c.pd_latency, s->c.sim_dt, 3 * n + 7, pdo);
+        for (int i = 0; i < n; i++) { q[i] = pdo[i]; qd[i] = pdo[n + i]; }
+    }
+    rexo_motor_torque(n, cmd, q, qd, qd_true, kp, kd, ta, to);   /* rex.py:596-600 */
     real tau[REXO_MAXDOF]; for (int j = 0; j < m->ndof; j++) tau[j] = 0;
     for (int i = 0; i < n; i++) {                                /* overheat protection rex.py:601-608 */
         if (fabs(ta[i]) > 2.45) e->overheat[i] += 1; else e->overheat[i] = 0;
@@ -695,6 +773,7 @@ static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {
         e->cmd[i] = cmd[i];
     }
     step_simulation(s, e, tau);
+    receive_observation(s, e);                                   /* rex.py:162 */
 }
 void rexo_substep(RexoSim* s, int i, const double* cmd) { apply_action_and_step(s, &s->env[i], cmd); }
 void rexo_physics_only(RexoSim* s, int i, const double* tau) {
@@ -815,7 +894,8 @@ static void turn_command(RexoSim* s, RexoEnv* e, const double* action, double* c
         return;
     }
     {   /* _check_target_position :324-332 */
-        real q4[4] = {e->quat[0], e->quat[1], e->quat[2], e->quat[3]}, rpy[3];
+        real q4[4], rpy[3];
+        sensed_quat(s, e, 7, q4);                                  /* rex.GetBaseOrientation() turn_env.py:325 */
         quat_to_euler(q4, rpy);
         double cz = rpy[2];
         if (cz < 0) cz += 6.28;
@@ -896,10 +976,15 @@ static double env_reward(RexoSim* s, RexoEnv* e) {
     else if (cx <= 0.05) fwd = 0.0;
     else fwd = cx / tp;
     double drift = -fabs(e->pos[1]);
-    real q4[4] = {e->quat[0], e->quat[1], e->quat[2], e->quat[3]}, R[9];
+    real q4[4], R[9];
+    sensed_quat(s, e, 3, q4);                                      /* rex.GetBaseOrientation() rex_gym_env.py:530 */
     quat_to_mat(q4, R);
     double shake = -fabs(1 * R[6] + 1 * R[7] + 0 * R[8]);
     double dot = 0;
+    if (s->sensor_on) {                                            /* GetMotorTorques() . GetMotorVelocities() :536-537 */
+        const double* co = ctrl_of(s, e); int n = s->m.nmotor;
+        for (int i = 0; i < n; i++) dot += (co[2 * n + i] + noise(s, e, 2, 4, i)) * (co[n + i] + noise(s, e, 1, 5, i));
+    } else
     for (int i = 0; i < s->m.nmotor; i++) dot += e->tau_obs[i] * e->qd[s->m.motor_dof[i]];
     double energy = -fabs(dot) * c->sim_dt;
     /* objectives [forward, energy, drift, shake] x weights [distance, energy, drift, shake] (:56-59,191,538-540) */
@@ -910,7 +995,9 @@ static int env_done(RexoSim* s, RexoEnv* e) {
     real q4[4] = {e->quat[0], e->quat[1], e->quat[2], e->quat[3]};
     if (c->task == REXO_TASK_POSES) return e->env_goal_reached;      /* is_fallen -> False (poses_env.py:247-254) */
     if (c->task == REXO_TASK_WALK || c->task == REXO_TASK_TURN) {    /* walk_env.py:326-338, rex_gym_env.py:490-495 */
-        real R[9]; quat_to_mat(q4, R);
+        real qs[4], R[9];
+        sensed_quat(s, e, 6, qs);                                    /* rex.GetBaseOrientation(): delayed + noisy */
+        quat_to_mat(qs, R);
         return (R[8] < 0.85) || e->env_goal_reached;
     }
     real rpy[3]; quat_to_euler(q4, rpy);
@@ -924,6 +1011,15 @@ static double map_pi(double a) {   /* MapToMinusPiToPi rex.py:26-41 */
     return r;
 }
 static void env_observation(RexoSim* s, RexoEnv* e, double* o) {   /* walk_env.py:356-362, gallop_env.py:349-356 */
+    if (s->sensor_on) {       /* GetBaseRollPitchYaw / GetBaseRollPitchYawRate / GetMotorAngles: delayed + noise (rex.py:429-442,548-558,457-468) */
+        const double* co = ctrl_of(s, e); int n = s->m.nmotor;
+        real d4[4] = {co[3 * n], co[3 * n + 1], co[3 * n + 2], co[3 * n + 3]}, rp[3];
+        quat_to_euler(d4, rp);
+        o[0] = rp[0] + noise(s, e, 3, 0, 0); o[1] = rp[1] + noise(s, e, 3, 0, 1);
+        o[2] = co[3 * n + 4] + noise(s, e, 4, 1, 0); o[3] = co[3 * n + 5] + noise(s, e, 4, 1, 1);
+        if (s->c.task == REXO_TASK_GALLOP) for (int i = 0; i < n; i++) o[4 + i] = map_pi(co[i] + noise(s, e, 0, 2, i));
+        return;
+    }
     real q4[4] = {e->quat[0], e->quat[1], e->quat[2], e->quat[3]}, rpy[3];
     quat_to_euler(q4, rpy);
     o[0] = rpy[0]; o[1] = rpy[1]; o[2] = e->angvel[0]; o[3] = e->angvel[1];
@@ -967,15 +1063,18 @@ static void settle_state(RexoSim* s, RexoEnv* e) {   /* Rex.Reset: rex.py:296-32
         e->overheat[i] = 0; e->enabled[i] = 1; e->tau_obs[i] = 0; e->cmd[i] = 0;
     }
     e->step_counter = 0;
+    if (s->sensor_on) { Hist* h = hist_of(s, e); h->len = 0; h->head = REXO_HIST - 1; }      /* _observation_history.clear() rex.py:303 */
     /* settle_on_reset == 2: pristine start -- joints placed at the task's init pose, no holding phase.  This is the state the
      * PyBullet trajectories recovered from the reference's checkpoints start from (tools/extract_memory_golden.py). */
     if (s->c.settle_on_reset == 2) for (int i = 0; i < m->nmotor; i++) e->q[m->motor_dof[i]] = s->init_pose[i];
     /* RexPosesEnv.reset calls RexGymEnv.reset() with initial_motor_angles=None: no holding phase (rex.py:307) */
     if (s->c.settle_on_reset == 1 && s->c.task != REXO_TASK_POSES) {
+        receive_observation(s, e);                                                       /* :313 */
         for (int it = 0; it < 100; it++) apply_action_and_step(s, e, s->stand_pose);     /* :315-318 */
         int n2 = (int)(0.5 / s->c.sim_dt);                                               /* reset_duration=0.5 */
         for (int it = 0; it < n2; it++) apply_action_and_step(s, e, s->init_pose);       /* :319-323 */
     }
+    receive_observation(s, e);                                                           /* :324 */
 }
 static void reset_env(RexoSim* s, int i) {
     RexoEnv* e = &s->env[i];
@@ -996,6 +1095,10 @@ static void reset_env(RexoSim* s, int i) {
         settle_state(s, snap); snap->reset_count = 1;
     }
     *e = *snap;
+    if (s->sensor_on) {       /* the history the reset hold left behind (it only depends on the field, like the settled state) */
+        s->hist[i] = s->hist[c->num_envs + field];
+        memcpy(s->ctrl[i], s->ctrl[c->num_envs + field], sizeof(double) * REXO_OBSW);
+    }
     e->reset_count = rc; e->field_id = field; e->kp = kp; e->kd = kd;
     e->env_step_counter = 0; e->limit_step = 0;
     e->gp_phi = 0; e->gp_last_time = 0; e->gp_alpha = 0;
@@ -1046,6 +1149,14 @@ RexoSim* rexo_create(const RexoModel* model, const RexoConfig* cfg) {
     s->env = (RexoEnv*)calloc(cfg->num_envs, sizeof(RexoEnv));
     s->nsnap = cfg->terrain == REXO_TERRAIN_RANDOM ? cfg->nfields : 1;
     s->snapshot = (RexoEnv*)calloc(s->nsnap, sizeof(RexoEnv));
+    s->sensor_on = cfg->control_latency > 0 || cfg->pd_latency > 0;
+    for (int k = 0; k < 5; k++) s->sensor_on |= cfg->noise_stdev[k] > 0;
+    {   /* rings exist when the sensor model is on, and always for small batches (unit entry points) */
+        int nh = (s->sensor_on || cfg->num_envs <= 64) ? cfg->num_envs + s->nsnap : 0;
+        s->hist = nh ? (Hist*)calloc(nh, sizeof(Hist)) : NULL;
+        s->ctrl = nh ? (double (*)[REXO_OBSW])calloc(nh, sizeof(double[REXO_OBSW])) : NULL;
+        for (int k = 0; k < nh; k++) s->hist[k].head = REXO_HIST - 1;
+    }
     switch (cfg->task) {
         case REXO_TASK_WALK: s->act_dim = cfg->signal == REXO_SIGNAL_IK ? 2 : 8; s->obs_dim = 4; break;
         case REXO_TASK_GALLOP: s->act_dim = cfg->signal == REXO_SIGNAL_IK ? 2 : 4; s->obs_dim = 4 + model->nmotor; break;
@@ -1065,7 +1176,12 @@ RexoSim* rexo_create(const RexoModel* model, const RexoConfig* cfg) {
     }
     return s;
 }
-void rexo_destroy(RexoSim* s) { if (!s) return; free(s->env); free(s->snapshot); free(s); }
+void rexo_destroy(RexoSim* s) { if (!s) return; free(s->env); free(s->snapshot); free(s->hist); free(s->ctrl); free(s); }
+void rexo_sensor_clear(RexoSim* s, int i) { if (s->hist) { s->hist[i].len = 0; s->hist[i].head = REXO_HIST - 1; } }
+void rexo_sensor_push(RexoSim* s, int i, const double* obs) { if (s->hist) hist_push(&s->hist[i], obs, 3 * s->m.nmotor + 7); }
+void rexo_sensor_delayed(RexoSim* s, int i, double latency, double* out) {
+    if (s->hist) hist_delayed(&s->hist[i], latency, s->c.sim_dt, 3 * s->m.nmotor + 7, out);
+}
 int rexo_obs_dim(const RexoSim* s) { return s->obs_dim; }
 int rexo_action_dim(const RexoSim* s) { return s->act_dim; }
 RexoEnv* rexo_env(RexoSim* s, int i) { return &s->env[i]; }
