@@ -103,6 +103,15 @@ typedef struct {
                                        * in its shipped checkpoint ran at about 16 (tests/test_pybullet_goldens.py) */
     float pose_values[5];             /* poses task: base_y, base_z, base_roll, base_pitch, base_yaw constructor arguments
                                        * (poses_env.py:49-53); all NaN = None: the pose rotates per reset, target drawn in range */
+    /* sensor model (rex_gym/model/rex.py:122,726-769; constructor arguments rex_gym_env.py:61,70-71).  All zero = the reference
+     * default: no history is kept and the kernels read the true state.  Otherwise every sub-step pushes the true observation
+     * [q, qd, observed torque, base quaternion, base angular velocity] into a per-env ring of the deque's depth (<= 100 rows);
+     * the PD loop reads it pd_latency ago, the controller / reward / termination / observation control_latency ago (linear
+     * blend of the two neighbouring rows), plus Gaussian noise.  np.random.normal (unseeded upstream) is replaced by a
+     * counter-based N(0,1) keyed on (seed, global env, reset count, control step, call site, component): include/rexsim.h
+     * rexsim_noise is the same generator host-side. */
+    double control_latency, pd_latency;   /* seconds */
+    double noise_stdev[5];                /* SENSOR_NOISE_STDDEV order (rex.py:22): motor angle, velocity, torque, base rpy, rpy rate */
 } RexSimConfig;
 
 typedef struct RexSim RexSim;
@@ -156,6 +165,13 @@ int64_t rexsim_launch_count(const RexSim* sim);
 /* the counter-based generator behind every reset draw (replaces Python's unseeded `random`,
  * walk_env.py:133-147, gallop_env.py:151, turn_env.py:138,147); host-callable so tests can pin it */
 uint32_t rexsim_rand_u32(uint64_t seed, uint32_t global_env, uint32_t reset_count, uint32_t slot);
+/* the N(0,1) draw behind the sensor noise (replaces the unseeded np.random.normal of Rex._AddSensorNoise, rex.py:763-769):
+ * Box-Muller on two draws of the generator above, slots 1024 + 2*((step*8 + site)*32 + comp) and +1.  Sites: 0 observation rpy,
+ * 1 observation rpy rate, 2 observation motor angles, 3 reward orientation, 4 reward torques, 5 reward velocities,
+ * 6 termination orientation, 7 turn goal-check orientation.  (float arithmetic, as on the device) */
+float rexsim_noise(uint64_t seed, uint32_t global_env, uint32_t reset_count, uint32_t control_step, uint32_t site, uint32_t comp);
+/* rows per env of the sensor history ring this configuration keeps (0: sensor model off) */
+int rexsim_history_depth(const RexSimConfig* cfg);
 const char* rexsim_last_error(void);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@ class RexSimConfig(C.Structure):
         ("toe_npts", C.c_int32), ("toe_margin", C.c_float),
         ("contact_breaking", C.c_float), ("link_damping", C.c_float), ("max_coordinate_velocity", C.c_float), ("env_offset", C.c_int32),
         ("gait_clock_scale", C.c_double), ("pose_values", C.c_float * 5),
+        ("control_latency", C.c_double), ("pd_latency", C.c_double), ("noise_stdev", C.c_double * 5),
     ]
 
 
@@ -39,7 +40,8 @@ AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_cr
 
 EXPORTS = ["rexsim_obs_dim", "rexsim_action_dim", "rexsim_state_words", "rexsim_create", "rexsim_destroy",
            "rexsim_step", "rexsim_step_host", "rexsim_host_out_bytes", "rexsim_rebalance", "rexsim_reset", "rexsim_get_state", "rexsim_set_state", "rexsim_state_buffers",
-           "rexsim_error_flags", "rexsim_clear_errors", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32"]
+           "rexsim_error_flags", "rexsim_clear_errors", "rexsim_last_command", "rexsim_launch_count", "rexsim_last_error", "rexsim_rand_u32",
+           "rexsim_noise", "rexsim_history_depth"]
 
 _LIB = None
 
@@ -80,6 +82,9 @@ def load():
     L.rexsim_last_error.restype = C.c_char_p
     L.rexsim_rand_u32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rexsim_rand_u32.restype = C.c_uint32
+    L.rexsim_noise.argtypes = [C.c_uint64] + [C.c_uint32] * 5
+    L.rexsim_noise.restype = C.c_float
+    L.rexsim_history_depth.argtypes = [C.POINTER(RexSimConfig)]
     # include/rexsim_agent.h
     cfgp = C.POINTER(RexAgentConfig)
     L.rexagent_policy_floats.argtypes = [cfgp]; L.rexagent_policy_floats.restype = C.c_int64

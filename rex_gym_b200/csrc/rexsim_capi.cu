@@ -30,6 +30,8 @@ struct RexSim {
     int32_t* d_cost = nullptr;
     int32_t* d_hist = nullptr;
     bool perm_valid = false;
+    float* d_ring = nullptr;           // sensor history [D][words][N] (sensor model only)
+    float* d_snap_ring = nullptr;      // [nsnap][D][words]
     float* d_act = nullptr;            // staging for rexsim_step_host
     uint8_t* d_out = nullptr;          // obs | reward | done (same layout as the host block)
     int A = 0, O = 0;
@@ -77,7 +79,25 @@ static int validate(const RexSimConfig* c) {
     if (c->terrain != REXSIM_TERRAIN_PLANE && c->terrain != REXSIM_TERRAIN_RANDOM) return fail(REXSIM_ERR_UNSUPPORTED, "terrain type");
     if (c->toe_npts <= 0 || c->toe_npts > REXSIM_MAX_TOE_PTS) return fail(REXSIM_ERR_MODEL, "toe_npts out of range");
     if (!(c->gait_clock_scale > 0)) return fail(REXSIM_ERR_INVALID, "gait_clock_scale must be positive (1 = simulation clock)");
+    if (!(c->control_latency >= 0) || !(c->pd_latency >= 0)) return fail(REXSIM_ERR_INVALID, "latencies must be >= 0");
+    for (int k = 0; k < 5; k++) if (!(c->noise_stdev[k] >= 0)) return fail(REXSIM_ERR_INVALID, "noise_stdev must be >= 0");
     return REXSIM_OK;
+}
+static bool sensor_on(const RexSimConfig* c) {
+    bool on = c->control_latency > 0 || c->pd_latency > 0;
+    for (int k = 0; k < 5; k++) on = on || c->noise_stdev[k] > 0;
+    return on;
+}
+int rexsim_history_depth(const RexSimConfig* c) {
+    if (!c || !sensor_on(c)) return 0;
+    // Rex._GetDelayedObservation reads history[n] and history[n + 1], n = int(latency / dt); once n + 1 reaches the deque's
+    // length (maxlen 100, rex.py:122) it reads the oldest row instead
+    const int n_ctl = (int)(c->control_latency / c->sim_dt_d), n_pd = (int)(c->pd_latency / c->sim_dt_d);
+    const int n = n_ctl > n_pd ? n_ctl : n_pd;
+    return n + 1 >= HIST_MAXLEN ? (int)HIST_MAXLEN : n + 2;
+}
+float rexsim_noise(uint64_t seed, uint32_t global_env, uint32_t reset_count, uint32_t control_step, uint32_t site, uint32_t comp) {
+    return noise_unit(seed, global_env, reset_count, control_step, site, comp);
 }
 
 int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_model_floats, RexSim** out) {
@@ -118,6 +138,22 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
     CK(cudaMalloc(&s->d_cost, (size_t)N * sizeof(int32_t)));
     CK(cudaMemset(s->d_cost, 0, (size_t)N * sizeof(int32_t)));
     CK(cudaMalloc(&s->d_hist, 256 * sizeof(int32_t)));
+    if (sensor_on(cfg)) {
+        Params& P = s->P;
+        const double dt = cfg->sim_dt_d;
+        P.sensor_on = 1;
+        P.ring_depth = rexsim_history_depth(cfg);
+        P.n_ctl = (int)(cfg->control_latency / dt); P.n_pd = (int)(cfg->pd_latency / dt);
+        P.a_ctl = (float)((cfg->control_latency - P.n_ctl * dt) / dt); P.a_pd = (float)((cfg->pd_latency - P.n_pd * dt) / dt);
+        P.lat_ctl = (float)cfg->control_latency; P.lat_pd = (float)cfg->pd_latency;
+        for (int k = 0; k < 5; k++) P.noise_sd[k] = (float)cfg->noise_stdev[k];
+        const size_t words = cfg->num_motors == 18 ? HW_WORDS_ARM : HW_WORDS;
+        CK(cudaMalloc(&s->d_ring, (size_t)P.ring_depth * words * N * sizeof(float)));
+        CK(cudaMemset(s->d_ring, 0, (size_t)P.ring_depth * words * N * sizeof(float)));
+        CK(cudaMalloc(&s->d_snap_ring, (size_t)s->nsnap * P.ring_depth * words * sizeof(float)));
+        CK(cudaMemset(s->d_snap_ring, 0, (size_t)s->nsnap * P.ring_depth * words * sizeof(float)));
+        P.ring = s->d_ring; P.snap_ring = s->d_snap_ring;
+    }
     s->A = rexsim_action_dim(cfg->task, cfg->signal); s->O = rexsim_obs_dim(cfg->task, cfg->num_motors);
     CK(cudaMalloc(&s->d_act, (size_t)N * s->A * sizeof(float)));
     CK(cudaMalloc(&s->d_out, (size_t)rexsim_host_out_bytes(s)));
@@ -154,6 +190,7 @@ int rexsim_create(const RexSimConfig* cfg, const float* model_tables, int32_t n_
 void rexsim_destroy(RexSim* s) {
     if (!s) return;
     cudaFree(s->d_model); cudaFree(s->d_sf); cudaFree(s->d_si); cudaFree(s->d_snap_f); cudaFree(s->d_snap_i);
+    cudaFree(s->d_ring); cudaFree(s->d_snap_ring);
     cudaFree(s->d_zoff); cudaFree(s->d_err); cudaFree(s->d_cmd); cudaFree(s->d_act); cudaFree(s->d_out); cudaFree(s->d_perm); cudaFree(s->d_cost); cudaFree(s->d_hist);
     delete s;
 }

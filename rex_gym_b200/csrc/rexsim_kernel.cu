@@ -77,6 +77,73 @@ __device__ __forceinline__ void quat_to_euler(float x, float y, float z, float w
     }
 }
 
+__device__ __forceinline__ void euler_to_quat(const float* rpy, float* q) {                        // pybullet getQuaternionFromEuler
+    float sr, cr, sp, cp, sy, cy;
+    sincosf(rpy[0] * 0.5f, &sr, &cr); sincosf(rpy[1] * 0.5f, &sp, &cp); sincosf(rpy[2] * 0.5f, &sy, &cy);
+    q[0] = sr * cp * cy - cr * sp * sy;
+    q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy;
+    q[3] = cr * cp * cy + sr * sp * sy;
+}
+
+// -------------------------------------------------------------------------------------------------
+// sensor model: observation history, latency, noise (rex_gym/model/rex.py:122,726-769)
+// -------------------------------------------------------------------------------------------------
+// One row per ReceiveObservation (= per sub-step) in a ring of P.ring_depth rows, ring[slot][word][env]; `push` counts the rows
+// since Rex.Reset cleared the deque (I_HPUSH), so history[k] (k = 0 newest) sits in slot (push - 1 - k) mod depth and the
+// deque's length is min(push, 100).  Every lane writes / reads the 9 words of its own leg; lane 0 writes the 7 base words
+// (and the arm's 18), which the other lanes read after a __syncwarp over the env's 4 lanes.
+struct Sensor { float* ring; int N, env, depth, words, push; uint32_t genv, rc; };
+
+template <bool ARM>
+__device__ __forceinline__ void sensor_push(Sensor& S, int leg, const Lane& L, const Arm& AR, bool valid) {
+    if (valid) {
+        float* r = S.ring + ((size_t)(S.push % S.depth) * S.words) * S.N + S.env;
+        const size_t N = (size_t)S.N;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            r[(9 * leg + j) * N] = L.q[j]; r[(9 * leg + 3 + j) * N] = L.qd[j]; r[(9 * leg + 6 + j) * N] = L.tau_obs[j];
+        }
+        if (leg == 0) {
+            r[(HW_BASE + 0) * N] = L.qx; r[(HW_BASE + 1) * N] = L.qy; r[(HW_BASE + 2) * N] = L.qz; r[(HW_BASE + 3) * N] = L.qw;
+            r[(HW_BASE + 4) * N] = L.w.x; r[(HW_BASE + 5) * N] = L.w.y; r[(HW_BASE + 6) * N] = L.w.z;
+            if (ARM) {
+#pragma unroll
+                for (int j = 0; j < ARM_NJ; j++) {
+                    r[(HW_ARM + j) * N] = AR.q[j]; r[(HW_ARM + 6 + j) * N] = AR.qd[j]; r[(HW_ARM + 12 + j) * N] = AR.tau_obs[j];
+                }
+            }
+        }
+    }
+    S.push++;
+    __syncwarp(env_mask());          // the base words of lane 0 are visible to the env's other lanes from here on
+}
+// Rex._GetDelayedObservation (rex.py:735-753) for one word of the row: n = int(latency / dt), a = (latency - n dt) / dt
+__device__ __forceinline__ float sensor_delayed(const Sensor& S, float latency, int n, float a, int word) {
+    const int len = min(S.push, (int)HIST_MAXLEN);
+    const float* base = S.ring + (size_t)word * S.N + S.env;
+    const size_t row = (size_t)S.words * S.N;
+    auto at = [&](int k) { return base[(size_t)((S.push - 1 - k) % S.depth) * row]; };
+    if (latency <= 0.f || len == 1) return at(0);
+    if (n + 1 >= len) return at(len - 1);
+    return (1.0f - a) * at(n) + a * at(n + 1);
+}
+__device__ __forceinline__ float sensor_noise(const Params& P, const Sensor& S, uint32_t step, int group, uint32_t site, uint32_t comp) {
+    const float sd = P.noise_sd[group];
+    if (sd <= 0.f) return 0.f;
+    return sd * noise_unit(P.cfg.seed, S.genv, S.rc, step, site, comp);
+}
+// Rex.GetBaseOrientation (rex.py:530-537): quaternion of (Euler angles of the DELAYED orientation + noise)
+__device__ __forceinline__ void sensed_quat(const Params& P, const Sensor& S, uint32_t step, uint32_t site, float* q4) {
+    float d4[4], rpy[3];
+#pragma unroll
+    for (int a = 0; a < 4; a++) d4[a] = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_BASE + a);
+    quat_to_euler(d4[0], d4[1], d4[2], d4[3], rpy);
+#pragma unroll
+    for (int a = 0; a < 3; a++) rpy[a] += sensor_noise(P, S, step, 3, site, a);
+    euler_to_quat(rpy, q4);
+}
+
 // 6x6 SPD inverse (symmetric storage m[i][j], i>=j used) via Cholesky, fully unrolled in registers
 struct Sym6 { float m[21]; };   // packed lower: idx(i,j) = i*(i+1)/2 + j
 __device__ __forceinline__ constexpr int ix(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
@@ -214,13 +281,14 @@ static __constant__ int c_seq_owner[27] = {0, 0, 0, 1, 1, 2, 2, 3, 3, 0, 0, 0, 0
 static __constant__ int c_seq_row[27] = {1, 4, 7, 4, 7, 4, 7, 4, 7, 2, 3, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9};
 
 // motor model + overheat (rex_gym/model/motor.py:76-143, rex_gym/model/rex.py:601-623) for one joint
-__device__ __forceinline__ float motor_torque(float cmd, float q, float qd, float kp, float kd, float& tau_obs) {
+// q, qd: what the PD loop sees (pd_latency ago, rex.py:755-759); qd_true: the motor's actual rate (back-EMF, motor.py:131)
+__device__ __forceinline__ float motor_torque(float cmd, float q, float qd, float qd_true, float kp, float kd, float& tau_obs) {
     const float V = 32.0f, R = 0.186f, Kt = 0.0954f;
     float pwm = -1.f * kp * (q - cmd) - kd * qd;
     pwm = fminf(fmaxf(pwm, -1.f), 1.f);
     const float VoR = V / R, invR = 1.0f / R;     // compile-time constants: the per-motor divisions become multiplies
     tau_obs = fminf(fmaxf(Kt * (pwm * VoR), -5.7f), 5.7f);
-    float vnet = fminf(fmaxf(pwm * V - Kt * qd, -50.f), 50.f);
+    float vnet = fminf(fmaxf(pwm * V - Kt * qd_true, -50.f), 50.f);
     float cur = vnet * invR;
     float mag = fabsf(cur), t;
     // np.interp over [0,10,...,60] -> [0,1,1.9,2.45,3.0,3.25,3.5]
@@ -853,11 +921,13 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
 // Rex.ApplyAction + stepSimulation (rex_gym/model/rex.py:158-163,568-641) for the own leg's three motors
 static __constant__ float c_arm_rest[6] = {-1.6f, -1.6f, 0.f, 0.f, 1.6f, 0.f};   // ARM_POSES['rest'] rex_constants.py:3-8
 
-template <int TERRAIN, bool ARM>
+template <int TERRAIN, bool ARM, bool SENSOR>
 __device__ __forceinline__ void apply_action_and_step(const Params& P, const float* sm, Lane& L, int leg,
-                                                      const float* cmd, float kp, float kd, Ground& G, Arm& AR) {
+                                                      const float* cmd, float kp, float kd, Ground& G, Arm& AR,
+                                                      Sensor& S, bool valid) {
     float tau[3];
     float tauA[ARM_NJ];
+    const bool pd_delayed = SENSOR && P.lat_pd > 0.f;        // _GetPDObservation (rex.py:755-759): q, qd as they were pd_latency ago
     if (ARM) {
 #pragma unroll
         for (int j = 0; j < ARM_NJ; j++) tauA[j] = 0.f;
@@ -866,7 +936,12 @@ __device__ __forceinline__ void apply_action_and_step(const Params& P, const flo
 #pragma unroll
             for (int j = 0; j < ARM_NJ; j++) {
                 float to;
-                float ta = motor_torque(c_arm_rest[j], AR.q[j], AR.qd[j], kp, kd, to);
+                float qo = AR.q[j], qdo = AR.qd[j];
+                if (pd_delayed) {
+                    qo = sensor_delayed(S, P.lat_pd, P.n_pd, P.a_pd, HW_ARM + j);
+                    qdo = sensor_delayed(S, P.lat_pd, P.n_pd, P.a_pd, HW_ARM + 6 + j);
+                }
+                float ta = motor_torque(c_arm_rest[j], qo, qdo, AR.qd[j], kp, kd, to);
                 uint32_t w = AR.ovh[j / 3], c = (w >> (10 * (j % 3))) & 1023u;
                 c = (fabsf(ta) > 2.45f) ? min(c + 1u, 1023u) : 0u;
                 if (c > limitA) AR.enabled &= ~(1u << j);
@@ -880,7 +955,12 @@ __device__ __forceinline__ void apply_action_and_step(const Params& P, const flo
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         float to;
-        float ta = motor_torque(cmd[j], L.q[j], L.qd[j], kp, kd, to);
+        float qo = L.q[j], qdo = L.qd[j];
+        if (pd_delayed) {
+            qo = sensor_delayed(S, P.lat_pd, P.n_pd, P.a_pd, 9 * leg + j);
+            qdo = sensor_delayed(S, P.lat_pd, P.n_pd, P.a_pd, 9 * leg + 3 + j);
+        }
+        float ta = motor_torque(cmd[j], qo, qdo, L.qd[j], kp, kd, to);
         uint32_t c = (L.ovh >> (10 * j)) & 1023u;
         c = (fabsf(ta) > 2.45f) ? min(c + 1u, 1023u) : 0u;
         if (c > limit) L.enabled &= ~(1u << j);
@@ -889,6 +969,7 @@ __device__ __forceinline__ void apply_action_and_step(const Params& P, const flo
         tau[j] = ((L.enabled >> j) & 1u) ? ta : 0.f;
     }
     physics_substep<TERRAIN, ARM>(P, sm, L, leg, tau, G, AR, tauA);
+    if (SENSOR) sensor_push<ARM>(S, leg, L, AR, valid);         // Rex.ReceiveObservation (rex.py:162,726-733)
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1020,7 +1101,8 @@ struct Task {
 
 // <task>._transform_action_to_motor_command for the own leg
 template <int TASK, int SIGNAL>
-__device__ __forceinline__ void task_command(const Params& P, Task& K, const Lane& L, int leg, const float* act, float* cmd) {
+__device__ __forceinline__ void task_command(const Params& P, Task& K, const Lane& L, int leg, const float* act, float* cmd,
+                                             const float* sq = nullptr /* sensed base quaternion (sensor model on), else the true one */) {
     const double dtd = P.cfg.sim_dt_d;
     const double t = __dmul_rn((double)K.step_counter, dtd);     // products via __dmul_rn: never contracted into FMAs
     float ip[3]; init_pose(SIGNAL, leg, ip);
@@ -1098,7 +1180,9 @@ __device__ __forceinline__ void task_command(const Params& P, Task& K, const Lan
             return;
         }
         {
-            float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
+            float rpy[3];
+            if (sq) quat_to_euler(sq[0], sq[1], sq[2], sq[3], rpy);            // rex.GetBaseOrientation() turn_env.py:325
+            else quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
             float cz = rpy[2];
             if (cz < 0.f) cz += 6.28f;
             if (fabsf(K.torient - cz) <= 0.01f) {
@@ -1227,7 +1311,8 @@ __device__ __forceinline__ void store_arm(float* sf, int32_t* si, int N, int env
 template <bool ARM>
 // `valid` is false on the padding lanes that replicate the last env to keep warps whole: they compute, but never write
 // (a replica that re-read the counter after the real lane's write would otherwise bump it twice)
-__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field, Arm& AR, bool valid) {
+__device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, int leg, Lane& L, Task& K, float& kp, float& kd, int& field, Arm& AR, bool valid,
+                                                    Sensor& S) {
     const RexSimConfig& c = P.cfg;
     const int N = P.N;
     uint32_t rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env] + 1u;
@@ -1280,9 +1365,21 @@ __device__ __forceinline__ void reset_from_snapshot(const Params& P, int env, in
         }
         K.flags = (K.flags & ~(7 << FL_POSE_SHIFT)) | (pose << FL_POSE_SHIFT);
     }
+    if (P.sensor_on) {
+        // the history the reset hold left behind only depends on the field, like the settled state: copy the snapshot's rows
+        // (same slots: the push count is copied with them).  Written by the env's own 4 lanes, read after the __syncwarp.
+        const int words = S.words, depth = S.depth;
+        S.push = si[I_HPUSH]; S.rc = rc;
+        if (valid) {
+            const float* src = P.snap_ring + (size_t)field * depth * words;
+            for (int t = leg; t < depth * words; t += 4) S.ring[(size_t)t * N + env] = src[t];
+        }
+        __syncwarp(env_mask());
+    }
     if (valid && leg == 0) {
         P.si[I_RESETCNT * (size_t)N + env] = (int32_t)rc;
         P.si[I_FIELD * (size_t)N + env] = field;
+        if (P.sensor_on) P.si[I_HPUSH * (size_t)N + env] = S.push;
         P.sf[F_KP * (size_t)N + env] = kp; P.sf[F_KD * (size_t)N + env] = kd;
         P.sf[F_TORIENT * (size_t)N + env] = K.torient; P.sf[F_IORIENT * (size_t)N + env] = K.iorient;
     }
@@ -1294,13 +1391,31 @@ __device__ __forceinline__ float map_pi(float a) {   // MapToMinusPiToPi rex.py:
     if (r >= PI_F) r -= TWO_PI; else if (r < -PI_F) r += TWO_PI;
     return r;
 }
-// _get_observation (+ RangeNormalize) for the env; lane 0 writes the 4 base terms, every lane its 3 angles (gallop)
-template <int TASK>
-__device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, const Lane& L, float* obs_row) {
-    float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
+// _get_observation (+ RangeNormalize) for the env; lane 0 writes the 4 base terms, every lane its 3 angles (gallop).
+// Sensor model on: GetBaseRollPitchYaw / GetBaseRollPitchYawRate / GetMotorAngles = delayed row + noise (rex.py:429-442,548-558,457-468)
+template <int TASK, bool SENSOR>
+__device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, const Lane& L, float* obs_row,
+                                          const Sensor& S, uint32_t step) {
+    float rpy[3];
+    float wx = L.w.x, wy = L.w.y;
+    float qa[3] = {L.q[0], L.q[1], L.q[2]};
+    if (SENSOR) {
+        float d4[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) d4[a] = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_BASE + a);
+        quat_to_euler(d4[0], d4[1], d4[2], d4[3], rpy);
+        rpy[0] += sensor_noise(P, S, step, 3, 0, 0); rpy[1] += sensor_noise(P, S, step, 3, 0, 1);
+        wx = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_BASE + 4) + sensor_noise(P, S, step, 4, 1, 0);
+        wy = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_BASE + 5) + sensor_noise(P, S, step, 4, 1, 1);
+        if (TASK == REXSIM_TASK_GALLOP) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                qa[j] = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, 9 * leg + j) + sensor_noise(P, S, step, 0, 2, 3 * leg + j);
+        }
+    } else quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
     const float two_pi = 6.283185307179586f;
     const float ub_ang = two_pi + 0.01f, ub_rate = (float)(2.0 * PI_D / P.cfg.sim_dt_d) + 0.01f;
-    float o[4] = {rpy[0], rpy[1], L.w.x, L.w.y};
+    float o[4] = {rpy[0], rpy[1], wx, wy};
     bool finite = true;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -1313,7 +1428,7 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
     if (TASK == REXSIM_TASK_GALLOP) {
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            float v = map_pi(L.q[j]);
+            float v = map_pi(qa[j]);
             finite = finite && isfinite(v);
             if (P.cfg.normalize) v = 2.f * (v + ub_ang) / (2.f * ub_ang) - 1.f;
             obs_row[4 + 3 * leg + j] = v;
@@ -1327,7 +1442,9 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
 // -------------------------------------------------------------------------------------------------
 // OCC = resident CTAs per SM the variant is compiled for: 1 -> 255 registers (lowest latency, small batches),
 // 4 -> 128 registers (16 warps/SM hide the serial PGS / ABA chains, large batches)
-template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM>
+// SENSOR: the observation-history / latency / noise model of Rex (rex.py:726-769) is compiled in (any latency or noise > 0);
+// the default build reads the true state and keeps no history.
+template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM, bool SENSOR>
 __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P) {
     __shared__ __align__(16) float sm[ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
@@ -1356,6 +1473,11 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     if (ARM && leg == 0) load_arm(P.sf, P.si, N, env, AR);
     float kp = P.sf[F_KP * (size_t)N + env], kd = P.sf[F_KD * (size_t)N + env];
     int field = P.si[I_FIELD * (size_t)N + env];
+    Sensor S;
+    S.ring = P.ring; S.N = N; S.env = env; S.depth = P.ring_depth; S.words = ARM ? HW_WORDS_ARM : HW_WORDS;
+    S.genv = (uint32_t)env + (uint32_t)c.env_offset;
+    S.push = 0; S.rc = 0u;
+    if (SENSOR) { S.push = P.si[I_HPUSH * (size_t)N + env]; S.rc = (uint32_t)P.si[I_RESETCNT * (size_t)N + env]; }
     Ground G;
     load_tile<TERRAIN>(P, field, L.pos, tiles + (TERRAIN == REXSIM_TERRAIN_RANDOM ? (threadIdx.x >> 2) * TILE_FLOATS : 0), G, leg);
 
@@ -1376,7 +1498,10 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
         act[j] = v;
     }
     float cmd[3];
-    task_command<TASK, SIGNAL>(P, K, L, leg, act, cmd);
+    if (SENSOR && TASK == REXSIM_TASK_TURN) {
+        float sq[4]; sensed_quat(P, S, (uint32_t)K.env_step, 7, sq);
+        task_command<TASK, SIGNAL>(P, K, L, leg, act, cmd, sq);
+    } else task_command<TASK, SIGNAL>(P, K, L, leg, act, cmd);
     if (valid) {
 #pragma unroll
         for (int j = 0; j < 3; j++) P.cmd_out[(size_t)(3 * leg + j) * N + env] = cmd[j];
@@ -1387,13 +1512,14 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // Rex.Step (rex.py:158-163)
     for (int r = 0; r < c.action_repeat; r++) {
-        apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, cmd, kp, kd, G, AR);
+        apply_action_and_step<TERRAIN, ARM, SENSOR>(P, sm, L, leg, cmd, kp, kd, G, AR, S, valid);
         K.step_counter += 1;
     }
     if (G.miss) L.err |= REXSIM_FLAG_TILE_MISS;
     // ---- reward (rex_gym_env.py:501-542; turn_env.py:362-367; standup_env.py:151-167) -----------------------
     float reward;
     M3 R = quat_to_mat(L.qx, L.qy, L.qz, L.qw);
+    const uint32_t ctl_step = (uint32_t)K.env_step;      // noise key of this step's reward / termination draws
     if (TASK == REXSIM_TASK_TURN) reward = 0.035f - fabsf(L.pos.x) - fabsf(L.pos.y);
     else if (TASK == REXSIM_TASK_POSES) reward = 1.0f;                // poses_env.py:256-258
     else if (TASK == REXSIM_TASK_STANDUP) {
@@ -1413,18 +1539,48 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
         else if (cx <= 0.05f) fwd = 0.0f;
         else fwd = cx / tp;
         float drift = -fabsf(L.pos.y);
-        float shake = -fabsf(R.c0.z + R.c1.z);          // rot_matrix[6] + rot_matrix[7]
-        float e = L.tau_obs[0] * L.qd[0] + L.tau_obs[1] * L.qd[1] + L.tau_obs[2] * L.qd[2];
-        if (ARM && leg == 0) {
+        float shake, e;
+        if (SENSOR) {
+            // rex.GetBaseOrientation() / GetMotorTorques() . GetMotorVelocities() (rex_gym_env.py:530-537): delayed row + noise
+            float sq[4]; sensed_quat(P, S, ctl_step, 3, sq);
+            M3 Rs = quat_to_mat(sq[0], sq[1], sq[2], sq[3]);
+            shake = -fabsf(Rs.c0.z + Rs.c1.z);
+            e = 0.f;
 #pragma unroll
-            for (int j = 0; j < ARM_NJ; j++) e = fmaf(AR.tau_obs[j], AR.qd[j], e);
+            for (int j = 0; j < 3; j++) {
+                const float to = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, 9 * leg + 6 + j) + sensor_noise(P, S, ctl_step, 2, 4, 3 * leg + j);
+                const float vo = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, 9 * leg + 3 + j) + sensor_noise(P, S, ctl_step, 1, 5, 3 * leg + j);
+                e = fmaf(to, vo, e);
+            }
+            if (ARM && leg == 0) {
+#pragma unroll
+                for (int j = 0; j < ARM_NJ; j++) {
+                    const float to = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_ARM + 12 + j) + sensor_noise(P, S, ctl_step, 2, 4, 12 + j);
+                    const float vo = sensor_delayed(S, P.lat_ctl, P.n_ctl, P.a_ctl, HW_ARM + 6 + j) + sensor_noise(P, S, ctl_step, 1, 5, 12 + j);
+                    e = fmaf(to, vo, e);
+                }
+            }
+        } else {
+            shake = -fabsf(R.c0.z + R.c1.z);          // rot_matrix[6] + rot_matrix[7]
+            e = L.tau_obs[0] * L.qd[0] + L.tau_obs[1] * L.qd[1] + L.tau_obs[2] * L.qd[2];
+            if (ARM && leg == 0) {
+#pragma unroll
+                for (int j = 0; j < ARM_NJ; j++) e = fmaf(AR.tau_obs[j], AR.qd[j], e);
+            }
         }
         float energy = -fabsf(sum4(e)) * (float)c.sim_dt_d;
         reward = fwd * c.w_distance + energy * c.w_energy + drift * c.w_drift + shake * c.w_shake;
     }
     // ---- termination ----------------------------------------------------------------------------------------
     bool done;
-    if (TASK == REXSIM_TASK_WALK || TASK == REXSIM_TASK_TURN) done = (R.c2.z < 0.85f) || (K.flags & FL_ENVGOAL);
+    if (TASK == REXSIM_TASK_WALK || TASK == REXSIM_TASK_TURN) {
+        float up = R.c2.z;
+        if (SENSOR) {                                   // is_fallen reads rex.GetBaseOrientation(): delayed + noisy (rex_gym_env.py:485-488)
+            float sq[4]; sensed_quat(P, S, ctl_step, 6, sq);
+            up = quat_to_mat(sq[0], sq[1], sq[2], sq[3]).c2.z;
+        }
+        done = (up < 0.85f) || (K.flags & FL_ENVGOAL);
+    }
     else if (TASK == REXSIM_TASK_POSES) done = false;                 // is_fallen() returns False (poses_env.py:247-254)
     else {
         float rpy[3]; quat_to_euler(L.qx, L.qy, L.qz, L.qw, rpy);
@@ -1437,7 +1593,7 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     bool finite = isfinite(reward) && isfinite(L.pos.x) && isfinite(L.pos.y) && isfinite(L.pos.z) &&
                   isfinite(L.q[0]) && isfinite(L.q[1]) && isfinite(L.q[2]) && isfinite(L.qd[0]) && isfinite(L.qd[1]) && isfinite(L.qd[2]);
     float* obs_row = P.obs + (size_t)env * O;
-    if (valid) finite = write_obs<TASK>(P, env, leg, L, obs_row) && finite;
+    if (valid) finite = write_obs<TASK, SENSOR>(P, env, leg, L, obs_row, S, (uint32_t)K.env_step) && finite;
     finite = (sum4(finite ? 0.f : 1.f) == 0.f);
     if (!finite) { L.err |= REXSIM_FLAG_NONFINITE; done = true; }
     int err = (int)or4((unsigned)L.err);
@@ -1452,11 +1608,12 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // ---- auto reset: done envs restart from the settled snapshot; obs = first observation of the new episode --
     if (c.auto_reset && done) {
-        reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, valid);
-        if (valid) write_obs<TASK>(P, env, leg, L, obs_row);
+        reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, valid, S);
+        if (valid) write_obs<TASK, SENSOR>(P, env, leg, L, obs_row, S, 0u);
     }
     store_lane(P.sf, P.si, N, env, leg, L, K, valid);
     if (ARM && valid && leg == 0) store_arm(P.sf, P.si, N, env, AR);
+    if (SENSOR && valid && leg == 0) P.si[I_HPUSH * (size_t)N + env] = S.push;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1478,8 +1635,14 @@ __global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_o
     const bool wr = valid && inrange;
     const int O = (TASK == REXSIM_TASK_GALLOP) ? 4 + 12 : 4;
     Lane L; Task K; Arm AR; float kp, kd; int field;
-    reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, wr);
-    if (wr && obs_out) write_obs<TASK>(P, env, leg, L, obs_out + (size_t)j * O);
+    Sensor S;
+    S.ring = P.ring; S.N = P.N; S.env = env; S.depth = P.ring_depth; S.words = ARM ? HW_WORDS_ARM : HW_WORDS;
+    S.genv = (uint32_t)env + (uint32_t)P.cfg.env_offset; S.push = 0; S.rc = 0u;
+    reset_from_snapshot<ARM>(P, env, leg, L, K, kp, kd, field, AR, wr, S);
+    if (wr && obs_out) {
+        if (P.sensor_on) write_obs<TASK, true>(P, env, leg, L, obs_out + (size_t)j * O, S, 0u);
+        else write_obs<TASK, false>(P, env, leg, L, obs_out + (size_t)j * O, S, 0u);
+    }
     if (wr && leg == 0) P.err[env] = 0;
     store_lane(P.sf, P.si, P.N, env, leg, L, K, wr);
     if (ARM && wr && leg == 0) store_arm(P.sf, P.si, P.N, env, AR);
@@ -1489,7 +1652,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const Params P, float* obs_o
 // settle kernel: Rex.Reset (rex.py:296-324) for one snapshot, 4 lanes: 100 sub-steps holding 'stand'
 // then reset_time/dt holding the task's init pose; writes the snapshot row
 // -------------------------------------------------------------------------------------------------
-template <int TERRAIN, bool ARM>
+template <int TERRAIN, bool ARM, bool SENSOR>
 __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_f, int32_t* snap_i, int signal, int task) {
     __shared__ __align__(16) float sm[ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
@@ -1517,10 +1680,18 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
     if (task == REXSIM_TASK_STANDUP) { ip[0] = (leg & 1) ? 0.4f : -0.4f; ip[1] = -1.5f; ip[2] = 6.f; }
     else init_pose(signal, leg, ip);
     // RexPosesEnv.reset -> RexGymEnv.reset(initial_motor_angles=None): Rex.Reset skips both holding phases (rex.py:307)
+    // sensor history of the reset hold: _observation_history.clear() (rex.py:303), one ReceiveObservation before the hold
+    // (:313), one per sub-step, one after it (:324).  The 8 replicas of the warp write identical rows to the same addresses.
+    Sensor S;
+    S.words = ARM ? HW_WORDS_ARM : HW_WORDS; S.depth = P.ring_depth;
+    S.ring = SENSOR ? P.snap_ring + (size_t)field * S.depth * S.words : nullptr;
+    S.N = 1; S.env = 0; S.push = 0; S.genv = 0u; S.rc = 0u;
     const int n1 = (task == REXSIM_TASK_POSES) ? 0 : 100;
-    for (int it = 0; it < n1; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
+    if (SENSOR && n1) sensor_push<ARM>(S, leg, L, AR, true);
+    for (int it = 0; it < n1; it++) apply_action_and_step<TERRAIN, ARM, SENSOR>(P, sm, L, leg, stand, P.cfg.motor_kp, P.cfg.motor_kd, G, AR, S, true);
     const int n2 = (task == REXSIM_TASK_POSES) ? 0 : (int)(0.5 / P.cfg.sim_dt_d);
-    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN, ARM>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G, AR);
+    for (int it = 0; it < n2; it++) apply_action_and_step<TERRAIN, ARM, SENSOR>(P, sm, L, leg, ip, P.cfg.motor_kp, P.cfg.motor_kd, G, AR, S, true);
+    if (SENSOR) sensor_push<ARM>(S, leg, L, AR, true);
     {
         float* qf = snap_f + (size_t)field * NF; int32_t* qi = snap_i + (size_t)field * NI;
         // snapshot rows are [NF] / [NI] with N = 1; the 8 replicas computed the same thing, the first one stores
@@ -1529,7 +1700,7 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
         int err = (int)or4((unsigned)L.err);
         if (threadIdx.x == 0) {
             qf[F_KP] = P.cfg.motor_kp; qf[F_KD] = P.cfg.motor_kd; qf[F_TORIENT] = 0.f; qf[F_IORIENT] = 0.f;
-            qi[I_RESETCNT] = 0; qi[I_FIELD] = field;
+            qi[I_RESETCNT] = 0; qi[I_FIELD] = field; qi[I_HPUSH] = S.push;
             if (err) { P.err[0] |= err; atomicOr(&P.err[P.N], err); }
         }
     }
@@ -1549,12 +1720,17 @@ static cudaError_t launch_step_tsa(const Params& P, cudaStream_t st) {
     int blocks = (P.N * 4 + threads - 1) / threads;
     // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover)
     const bool big = !ARM && blocks > 4 * P.sm_count;
+    if (P.sensor_on) {        // sensor model compiled in: one (255-register) build per terrain
+        if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM, true><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM, true><<<blocks, threads, 0, st>>>(P);
+        return cudaGetLastError();
+    }
     if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM><<<blocks, threads, 0, st>>>(P);
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM, false><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM, false><<<blocks, threads, 0, st>>>(P);
     } else {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM><<<blocks, threads, 0, st>>>(P);
+        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM, false><<<blocks, threads, 0, st>>>(P);
+        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM, false><<<blocks, threads, 0, st>>>(P);
     }
     return cudaGetLastError();
 }
@@ -1680,14 +1856,19 @@ cudaError_t launch_reset(const Params& P, float* obs_out, cudaStream_t st) {
     else reset_kernel<REXSIM_TASK_WALK, false><<<blocks, threads, 0, st>>>(P, obs_out);
     return cudaGetLastError();
 }
+template <int TERRAIN, bool ARM>
+static void launch_settle_ta(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st) {
+    if (P.sensor_on) settle_kernel<TERRAIN, ARM, true><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+    else settle_kernel<TERRAIN, ARM, false><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+}
 cudaError_t launch_settle(const Params& P, float* snap_f, int32_t* snap_i, cudaStream_t st) {
     const bool arm = P.cfg.num_motors == 18;
     if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
-        if (arm) settle_kernel<REXSIM_TERRAIN_PLANE, true><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
-        else settle_kernel<REXSIM_TERRAIN_PLANE, false><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+        if (arm) launch_settle_ta<REXSIM_TERRAIN_PLANE, true>(P, snap_f, snap_i, st);
+        else launch_settle_ta<REXSIM_TERRAIN_PLANE, false>(P, snap_f, snap_i, st);
     } else {
-        if (arm) settle_kernel<REXSIM_TERRAIN_RANDOM, true><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
-        else settle_kernel<REXSIM_TERRAIN_RANDOM, false><<<1, 32, 0, st>>>(P, snap_f, snap_i, P.cfg.signal, P.cfg.task);
+        if (arm) launch_settle_ta<REXSIM_TERRAIN_RANDOM, true>(P, snap_f, snap_i, st);
+        else launch_settle_ta<REXSIM_TERRAIN_RANDOM, false>(P, snap_f, snap_i, st);
     }
     return cudaGetLastError();
 }

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include "../../include/rexsim.h"
 
 namespace rexsim {
@@ -32,8 +33,13 @@ enum {
 enum {
     I_STEP = 0, I_ENVSTEP = 1, I_FLAGS = 2, I_RESETCNT = 3, I_FIELD = 4, I_ENDSTEP = 5, I_GPLAST = 6,
     I_PHI_LO = 7, I_PHI_HI = 8, I_OVH = 9 /*4 words, 3x10-bit counters per leg*/, I_CONTACT = 13,
-    I_OVHA = 14 /*2 words, 3x10-bit counters of the arm motors*/, NI = 16
+    I_OVHA = 14 /*2 words, 3x10-bit counters of the arm motors*/,
+    I_HPUSH = 16 /*observations pushed into the sensor history since Rex.Reset cleared it (sensor model only)*/, NI = 17
 };
+// sensor history ring (rex_gym/model/rex.py:122,726-753): one row per ReceiveObservation = per sub-step, words per env:
+//   [9*leg + 0..2] q, [+3..5] qd, [+6..8] observed torque of leg `leg`; [36..39] base quaternion, [40..42] base angular velocity;
+//   mark 'arm': [43..48] arm q, [49..54] arm qd, [55..60] arm observed torque.   Layout ring[slot][word][env].
+enum { HW_BASE = 36, HW_ARM = 43, HW_WORDS = 43, HW_WORDS_ARM = 61, HIST_MAXLEN = 100 };
 enum {
     FL_GOAL = 1, FL_TERMINATING = 2, FL_STILL = 4, FL_BACKWARDS = 8, FL_CLOCKWISE = 16, FL_ENVGOAL = 32,
     FL_ENABLED_SHIFT = 8,  // 12 leg motor-enabled bits
@@ -62,6 +68,15 @@ struct Params {
     int32_t sm_count;                  // SMs of the device (kernel variant choice)
     const int32_t* __restrict__ perm;  // [N] slot -> env (null: identity); see rexsim_rebalance
     int32_t* __restrict__ cost;        // [N] solver iterations of the last control step
+    // sensor model (control / PD latency, observation noise: rex.py:735-769); all unused when sensor_on == 0
+    int32_t sensor_on;
+    int32_t ring_depth;                // D rows kept per env: max(n_ctl, n_pd) + 2 (100 = the deque's maxlen when a latency reaches it)
+    float* ring;                       // [D][HW_WORDS(_ARM)][N]; NOT __restrict__: lanes of an env read what lane 0 wrote
+    float* snap_ring;                  // [nsnap][D][HW_WORDS(_ARM)] history the reset hold leaves behind, per field
+    int32_t n_ctl, n_pd;               // int(latency / dt)
+    float a_ctl, a_pd;                 // blend weight (latency - n dt) / dt of the older sample
+    float lat_ctl, lat_pd;             // the latencies themselves (only their sign is used on the device)
+    float noise_sd[5];                 // SENSOR_NOISE_STDDEV order: motor angle, motor velocity, motor torque, base rpy, base rpy rate
 };
 
 // ----- tiny vector algebra ---------------------------------------------------------------------------
@@ -188,6 +203,13 @@ __host__ __device__ __forceinline__ uint32_t rand_u32(uint64_t seed, uint32_t en
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z = z ^ (z >> 31);
     return (uint32_t)(z >> 32);
+}
+// counter-based N(0,1): Box-Muller on two draws of the reset generator (oracle rexo_noise in fp64; include/rexsim.h rexsim_noise is this function)
+__host__ __device__ __forceinline__ float noise_unit(uint64_t seed, uint32_t genv, uint32_t rc, uint32_t step, uint32_t site, uint32_t comp) {
+    const uint32_t slot = 1024u + (((step * 8u + site) * 32u + comp) << 1);
+    const float u1 = ((float)(rand_u32(seed, genv, rc, slot) >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(rand_u32(seed, genv, rc, slot + 1u) >> 8) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
 }
 __device__ __forceinline__ double rand_uniform(uint64_t seed, uint32_t env, uint32_t rc, uint32_t slot, double a, double b) {
     double u = (double)(rand_u32(seed, env, rc, slot) >> 8) * (1.0 / 16777216.0);

@@ -29,6 +29,7 @@ ACTION_BOUND = {("walk", "ik"): 0.4, ("walk", "ol"): 0.01, ("gallop", "ik"): 0.4
                 ("poses", "ik"): 0.1, ("poses", "ol"): 0.1}
 
 ERR_NONFINITE, ERR_JOINT_LIMIT, ERR_BODY_CONTACT, ERR_TILE_MISS, ERR_BAD_INDEX = 1, 2, 4, 8, 16
+SENSOR_NOISE_STDDEV = (0.0, 0.0, 0.0, 0.0, 0.0)      # rex_gym/model/rex.py:22, default of rex_gym_env.py:61
 
 
 class _DevArray(object):
@@ -86,7 +87,7 @@ class BatchedRexEnv(object):
                  normalize=False, max_episode_steps=0, auto_reset=False, seed=1234,
                  motor_kp_range=None, motor_kd_range=None, num_fields=64, solver_iterations=None, env_offset=0,
                  base_y=None, base_z=None, base_roll=None, base_pitch=None, base_yaw=None, gait_clock_scale=1.0,
-                 rebalance_every=8):
+                 rebalance_every=8, observation_noise_stdev=SENSOR_NOISE_STDDEV):
         if urdf_version is not None and urdf_version != DEFAULT_URDF_VERSION:
             raise ValueError("%s is not a supported urdf_version." % urdf_version)     # rex_gym_env.py:317-318
         if task not in TASKS or signal_type not in SIGNALS:
@@ -96,8 +97,8 @@ class BatchedRexEnv(object):
                              "pybullet_data pip package)" % terrain_type)
         if render or on_rack:
             raise ValueError("render / on_rack are GUI debugging modes of the reference; not part of the batched path")
-        if control_latency or pd_latency:
-            raise ValueError("sensor latency is not built (reference default 0)")
+        if control_latency < 0 or pd_latency < 0 or len(observation_noise_stdev) != 5 or min(observation_noise_stdev) < 0:
+            raise ValueError("control_latency / pd_latency must be >= 0 and observation_noise_stdev five values >= 0")
         if env_randomizer:
             raise ValueError("env_randomizer hooks are Python callbacks; use motor_kp_range / motor_kd_range")
         if not torch.cuda.is_available():
@@ -134,6 +135,10 @@ class BatchedRexEnv(object):
         c.gait_clock_scale = float(gait_clock_scale)     # GaitPlanner clock / simulation clock (the reference reads the wall clock)
         for k, v in enumerate((base_y, base_z, base_roll, base_pitch, base_yaw)):      # poses_env.py:49-53 (None = rotate per reset)
             c.pose_values[k] = float("nan") if v is None else float(v)
+        # sensor model (rex_gym_env.py:61,70-71 -> Rex(control_latency, pd_latency, observation_noise_stdev), rex.py:726-769)
+        c.control_latency, c.pd_latency = float(control_latency), float(pd_latency)
+        for k, v in enumerate(observation_noise_stdev):
+            c.noise_stdev[k] = float(v)
         self._fields = None
         with torch.cuda.device(self.device):
             if terrain_type == "random":

@@ -35,7 +35,7 @@ def test_host_only_entry_points():
     cfg = _capi.RexSimConfig()
     nf, ni = C.c_int32(), C.c_int32()
     assert L.rexsim_state_words(C.byref(cfg), C.byref(nf), C.byref(ni)) == 0
-    assert nf.value == 55 and ni.value == 16
+    assert nf.value == 55 and ni.value == 17          # + I_HPUSH (rows pushed into the sensor history)
 
 
 def test_create_rejects_bad_arguments_without_touching_the_gpu():
@@ -63,6 +63,45 @@ def test_rng_is_bit_identical_to_the_oracle():
     for _ in range(500):
         s, e, r, k = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**31)), int(rng.integers(0, 2**31)), int(rng.integers(0, 8))
         assert L.rexsim_rand_u32(s, e, r, k) == R.rexo_rand_u32(s, e, r, k)
+
+
+def test_sensor_noise_generator_matches_the_oracle():
+    """Rex._AddSensorNoise (rex.py:763-769) draws from the unseeded np.random.normal; both sides replace it by the same
+    counter-based Box-Muller draw.  The library evaluates it in float (as the device does), the oracle in double."""
+    from rex_gym_b200 import _capi
+    from oracle import oracle as O
+    L, R = _capi.load(), O.lib()
+    rng = np.random.default_rng(1)
+    got, want = [], []
+    for _ in range(4000):
+        s, e, r = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**20)), int(rng.integers(1, 2**16))
+        st, site, comp = int(rng.integers(0, 3000)), int(rng.integers(0, 8)), int(rng.integers(0, 18))
+        got.append(L.rexsim_noise(s, e, r, st, site, comp)); want.append(R.rexo_noise(s, e, r, st, site, comp))
+    got, want = np.array(got), np.array(want)
+    assert np.abs(got - want).max() < 5e-6
+    assert abs(want.mean()) < 0.06 and abs(want.std() - 1.0) < 0.05          # N(0, 1)
+
+
+def test_sensor_history_depth_follows_the_deque_reads():
+    """_GetDelayedObservation (rex.py:735-753) reads history[n] and history[n + 1], n = int(latency / dt); the deque keeps 100."""
+    from rex_gym_b200 import _capi
+    L = _capi.load()
+    cfg = _capi.RexSimConfig()
+    cfg.sim_dt_d = 0.001
+    assert L.rexsim_history_depth(C.byref(cfg)) == 0                       # reference default: no history at all
+    cfg.noise_stdev[3] = 0.01
+    assert L.rexsim_history_depth(C.byref(cfg)) == 2
+    cfg.control_latency, cfg.pd_latency = 0.02, 0.003
+    assert L.rexsim_history_depth(C.byref(cfg)) == 22
+    cfg.pd_latency = 0.0305
+    assert L.rexsim_history_depth(C.byref(cfg)) == 32
+    cfg.control_latency = 0.2
+    assert L.rexsim_history_depth(C.byref(cfg)) == 100
+    cfg.control_latency = -1.0
+    cfg.num_envs, cfg.num_motors, cfg.action_repeat, cfg.solver_iterations, cfg.toe_npts, cfg.gait_clock_scale = 8, 12, 5, 60, 27, 1.0
+    h = C.c_void_p()
+    tb = np.zeros(952, np.float32)
+    assert L.rexsim_create(C.byref(cfg), tb.ctypes.data, 952, C.byref(h)) == -1 and b"latenc" in L.rexsim_last_error()
 
 
 def test_model_table_packer_layout():
