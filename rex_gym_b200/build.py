@@ -44,7 +44,11 @@ def _run(cmd):
     return r.returncode, r.stdout, cmd
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=(), units=None):
+    """variant / defines: developer A/B builds -- librexsim_<variant>.so compiled with extra -D flags, loaded through
+    REXSIM_LIB (rex_gym_b200/_capi.py); the product library is the plain call."""
+    if variant:
+        return _build_variant(variant, list(defines), verbose, units)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -79,6 +83,44 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_variant(variant, defines, verbose, units=None):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    obj = os.path.join(OBJ, variant)
+    os.makedirs(obj, exist_ok=True)
+    lib = os.path.join(HERE, "librexsim_%s.so" % variant)
+    extra = (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines]
+    jobs, objs = [], []
+    for u in KERNEL_UNITS:
+        o = os.path.join(obj, "kernel_u%d.o" % u)
+        objs.append(o)
+        if units is not None and u not in units and os.path.exists(os.path.join(OBJ, "kernel_u%d.o" % u)):
+            objs[-1] = os.path.join(OBJ, "kernel_u%d.o" % u)       # untouched units: reuse the product objects
+            continue
+        jobs.append([nvcc] + NVCC_FLAGS + extra + ["-DREXSIM_UNIT=%d" % u, "-c", os.path.join(CSRC, "rexsim_kernel.cu"), "-o", o])
+    for f in OTHER_SOURCES:
+        objs.append(os.path.join(OBJ, f.replace(".cu", ".o")))
+    with ThreadPoolExecutor(min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(_run, jobs))
+    for rc, log, cmd in results:
+        if verbose:
+            print(log)
+        if rc != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + log)
+            raise RuntimeError("nvcc failed building " + lib)
+    rc, log, cmd = _run([nvcc] + ARCH_FLAGS + ["-shared", "-o", lib] + objs)
+    if rc != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("link failed: " + lib)
+    return lib
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--variant")
+    ap.add_argument("-D", action="append", default=[])
+    ap.add_argument("--units", type=lambda t: [int(x) for x in t.split(",")])
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.v, variant=a.variant, defines=a.D, units=a.units))

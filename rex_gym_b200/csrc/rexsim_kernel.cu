@@ -2,6 +2,7 @@
 #include "rexsim_kernel.cuh"
 #include "rexsim_arm.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace rexsim {
 
@@ -9,8 +10,26 @@ namespace rexsim {
 #ifndef REXSIM_MIN_BLOCKS
 #define REXSIM_MIN_BLOCKS 1
 #endif
+// threads per CTA: small-batch (255-register) build / large-batch (128-register) build.  The warps of a CTA re-align at every
+// sub-step, so a larger CTA shares more of the instruction stream -- see REXSIM_SYNC_SUBSTEP below
 #ifndef REXSIM_BLOCK
 #define REXSIM_BLOCK 128
+#endif
+#ifndef REXSIM_BLOCK_BIG
+#define REXSIM_BLOCK_BIG 256
+#endif
+// fast-path PGS formulation: 1 = pre-scaled row sums + lane-local residual (no per-iteration reduction), 0 = the round-1 form
+#ifndef REXSIM_PGS_FAST
+#define REXSIM_PGS_FAST 1
+#endif
+// resident CTAs per SM of the large-batch build (register cap 65536 / (128 * REXSIM_OCC_BIG))
+#ifndef REXSIM_OCC_BIG
+#define REXSIM_OCC_BIG 4
+#endif
+// 1: the warps of a CTA re-align at every sub-step (__syncthreads) so that the ~200 KB of straight-line per-sub-step code is
+// fetched once per CTA instead of once per warp (the kernel is instruction-fetch bound: ncu no_instruction stalls)
+#ifndef REXSIM_SYNC_SUBSTEP
+#define REXSIM_SYNC_SUBSTEP 1
 #endif
 #define PI_F 3.14159265358979323846f
 #define PI_D 3.14159265358979323846
@@ -671,9 +690,63 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         // ---- PGS in impulse space, Bullet row order: normals 0..3, then (t1,t2) of contacts 0..3 -----------
         // Each lane keeps only its own three impulses and the running row sums rs[d] = sum_j A[d][j] lambda_j;
         // the owner of a row broadcasts its impulse CHANGE and every lane folds it into its sums (3 FMA).
-        float lam[3] = {0.f, 0.f, 0.f}, rs[3] = {0.f, 0.f, 0.f};
+        float lam[3] = {0.f, 0.f, 0.f};
         bool running = true;             // env-uniform: the 4 lanes of an env leave the loop together
         const bool mine = active;
+#if REXSIM_PGS_FAST
+        // Row sums are kept pre-scaled: t[d] = rhs[d] - dinv[d] * sum_j A[d][j] lambda_j IS the next impulse change of row d, so
+        // the serial chain per row is clamp -> shuffle -> one FMA.  Every lane sees every impulse change (the broadcast), so
+        // with the 12 row denominators replicated once per sub-step each lane evaluates the iteration's residual itself:
+        // no reduction (two dependent shuffles) at the end of every iteration.  Same max, same early-out decision on all lanes.
+        float t[3] = {rhs[0], rhs[1], rhs[2]};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int cc = 0; cc < 12; cc++) A[r][cc] *= -dinv[r];
+        float denAll[4][3];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) denAll[s][d] = bcast4(den[d], s);
+        for (int it = 0; it < iters && running; it++) {
+            L.cost++;
+            float resid = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                float dI = t[0];
+                if (lam[0] + dI < 0.f) dI = -lam[0];
+                const bool upd = mine && (leg == s);
+                dI = upd ? dI : 0.f;
+                lam[0] += dI;
+                const float dl = bcast4(dI, s);
+                const float rr = dl * denAll[s][0]; resid = fmaxf(resid, rr * rr);
+                t[0] = fmaf(A[0][3 * s], dl, t[0]); t[1] = fmaf(A[1][3 * s], dl, t[1]); t[2] = fmaf(A[2][3 * s], dl, t[2]);
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const float lim = mu * lam[0];
+                const bool upd = mine && (leg == s) && (lam[0] > 0.f);
+                float dI1 = t[1];
+                const float sum1 = lam[1] + dI1;
+                if (sum1 < -lim) dI1 = -lim - lam[1]; else if (sum1 > lim) dI1 = lim - lam[1];
+                dI1 = upd ? dI1 : 0.f;
+                lam[1] += dI1;
+                float dI2 = fmaf(A[2][3 * s + 1], dI1, t[2]);            // own lane: column 3*leg+1 == 3*s+1 when upd
+                const float sum2 = lam[2] + dI2;
+                if (sum2 < -lim) dI2 = -lim - lam[2]; else if (sum2 > lim) dI2 = lim - lam[2];
+                dI2 = upd ? dI2 : 0.f;
+                lam[2] += dI2;
+                const float dl1 = bcast4(dI1, s), dl2 = bcast4(dI2, s);
+                const float r1 = dl1 * denAll[s][1], r2 = dl2 * denAll[s][2];
+                resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
+                t[0] = fmaf(A[0][3 * s + 2], dl2, fmaf(A[0][3 * s + 1], dl1, t[0]));
+                t[1] = fmaf(A[1][3 * s + 2], dl2, fmaf(A[1][3 * s + 1], dl1, t[1]));
+                t[2] = fmaf(A[2][3 * s + 2], dl2, fmaf(A[2][3 * s + 1], dl1, t[2]));
+            }
+            if (resid <= thr) running = false;
+        }
+#else
+        float rs[3] = {0.f, 0.f, 0.f};
         for (int it = 0; it < iters && running; it++) {
             L.cost++;
             float resid = 0.f;
@@ -715,6 +788,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             resid = max4(resid);
             if (resid <= thr) running = false;
         }
+#endif
         // ---- apply the net contact impulse: one more response pass -----------------------------------------
         const float ln = lam[0], l1 = lam[1], l2 = lam[2];
         float e1 = ln * uD1[0] + l1 * uD1[1] + l2 * uD1[2];
@@ -1444,11 +1518,12 @@ __device__ __forceinline__ bool write_obs(const Params& P, int env, int leg, con
 // 4 -> 128 registers (16 warps/SM hide the serial PGS / ABA chains, large batches)
 // SENSOR: the observation-history / latency / noise model of Rex (rex.py:726-769) is compiled in (any latency or noise > 0);
 // the default build reads the true state and keeps no history.
-template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM, bool SENSOR>
-__global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P) {
+extern __shared__ __align__(16) float dyn_smem[];      // heightfield tiles, (BLOCK / 4) x TILE_FLOATS floats (random terrain only)
+template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM, bool SENSOR, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (OCC * 128) / BLOCK) step_kernel(const Params P) {
     __shared__ __align__(16) float sm[ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ float tiles[TERRAIN == REXSIM_TERRAIN_RANDOM ? (REXSIM_BLOCK / 4) * TILE_FLOATS : 1];
+    float* tiles = dyn_smem;
     tma_load_tables(sm, P.model, (ARM ? REXSIM_MT_FLOATS_ARM : REXSIM_MT_FLOATS) * 4, &bar);
 
     const int N = P.N;
@@ -1512,6 +1587,9 @@ __global__ void __launch_bounds__(REXSIM_BLOCK, OCC) step_kernel(const Params P)
     }
     // Rex.Step (rex.py:158-163)
     for (int r = 0; r < c.action_repeat; r++) {
+#if REXSIM_SYNC_SUBSTEP
+        __syncthreads();
+#endif
         apply_action_and_step<TERRAIN, ARM, SENSOR>(P, sm, L, leg, cmd, kp, kd, G, AR, S, valid);
         K.step_counter += 1;
     }
@@ -1714,25 +1792,39 @@ __global__ void __launch_bounds__(32) settle_kernel(const Params P, float* snap_
 // dispatcher); rex_gym_b200/build.py runs the units in parallel.  Without REXSIM_UNIT everything is one unit.
 // -------------------------------------------------------------------------------------------------
 #if !defined(REXSIM_UNIT) || REXSIM_UNIT < 100
+template <int TASK, int SIGNAL, int TERRAIN, int OCC, bool ARM, bool SENSOR, int BLOCK>
+static cudaError_t launch_step_variant(const Params& P, cudaStream_t st) {
+    auto kern = step_kernel<TASK, SIGNAL, TERRAIN, OCC, ARM, SENSOR, BLOCK>;
+    const int blocks = (P.N * 4 + BLOCK - 1) / BLOCK;
+    const size_t smem = TERRAIN == REXSIM_TERRAIN_RANDOM ? (size_t)(BLOCK / 4) * TILE_FLOATS * sizeof(float) : 0;
+    if (smem > 48 * 1024) {        // opt in once per kernel (the attribute is sticky)
+        static bool done = false;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+    }
+    kern<<<blocks, BLOCK, smem, st>>>(P);
+    return cudaGetLastError();
+}
+template <int TASK, int SIGNAL, int TERRAIN, bool ARM>
+static cudaError_t launch_step_tsta(const Params& P, cudaStream_t st) {
+    // sensor model compiled in: one (255-register) build per terrain
+    if (P.sensor_on) return launch_step_variant<TASK, SIGNAL, TERRAIN, 1, ARM, true, REXSIM_BLOCK>(P, st);
+    // Beyond one wave of 2-CTA/SM residency (128-thread CTAs; two waves on heightfields): the 128-register build (16 warps/SM
+    // hide the serial ABA / PGS chains) in larger CTAs; below that the 255-register build, lowest single-wave latency.
+    // Measured crossovers (walk-ik flat 4096 / 16 384 envs: 0.142 / 0.229 ms small, 0.172 / 0.211 ms large; gallop-ol 16 384:
+    // 0.257 / 0.206; turn-ik heightfield 16 384: 0.952 / 1.035), DESIGN.md section 5.
+    bool big = !ARM && (P.N * 4 + 127) / 128 > (TERRAIN == REXSIM_TERRAIN_PLANE ? 2 : 4) * P.sm_count;
+    if (const char* f = getenv("REXSIM_FORCE_BUILD")) big = !ARM && f[0] == 'b';      // developer A/B: "big" / "small"
+    if (big) return launch_step_variant<TASK, SIGNAL, TERRAIN, ARM ? 1 : REXSIM_OCC_BIG, ARM, false, ARM ? REXSIM_BLOCK : REXSIM_BLOCK_BIG>(P, st);
+    return launch_step_variant<TASK, SIGNAL, TERRAIN, 1, ARM, false, REXSIM_BLOCK>(P, st);
+}
 template <int TASK, int SIGNAL, bool ARM>
 static cudaError_t launch_step_tsa(const Params& P, cudaStream_t st) {
-    int threads = REXSIM_BLOCK;
-    int blocks = (P.N * 4 + threads - 1) / threads;
-    // more than two waves of 2-CTA/SM residency: switch to the 128-register build (measured crossover)
-    const bool big = !ARM && blocks > 4 * P.sm_count;
-    if (P.sensor_on) {        // sensor model compiled in: one (255-register) build per terrain
-        if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM, true><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM, true><<<blocks, threads, 0, st>>>(P);
-        return cudaGetLastError();
-    }
-    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM ? 1 : 4, ARM, false><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, 1, ARM, false><<<blocks, threads, 0, st>>>(P);
-    } else {
-        if (big) step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM ? 1 : 4, ARM, false><<<blocks, threads, 0, st>>>(P);
-        else step_kernel<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, 1, ARM, false><<<blocks, threads, 0, st>>>(P);
-    }
-    return cudaGetLastError();
+    if (P.cfg.terrain == REXSIM_TERRAIN_PLANE) return launch_step_tsta<TASK, SIGNAL, REXSIM_TERRAIN_PLANE, ARM>(P, st);
+    return launch_step_tsta<TASK, SIGNAL, REXSIM_TERRAIN_RANDOM, ARM>(P, st);
 }
 template <int TASK, int SIGNAL>
 static cudaError_t launch_step_ts(const Params& P, cudaStream_t st) {
