@@ -13,6 +13,7 @@
 namespace rexsim {
 
 #define ARM_NJ 6
+#define ARM_KA 3          // arm joint-limit rows the fast solver path carries (the rest pose violates exactly three: joints 0, 1, 4)
 // model-table layout of one arm body (REXSIM_MT_ARM + 32*j): jpos[3] jrot[9] axis[3] mass com[3] inertia[6] lower upper
 #define ARM_STRIDE 32
 

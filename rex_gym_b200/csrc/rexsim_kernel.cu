@@ -2,6 +2,7 @@
 #include "rexsim_kernel.cuh"
 #include "rexsim_arm.cuh"
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace rexsim {
@@ -17,10 +18,6 @@ namespace rexsim {
 #endif
 #ifndef REXSIM_BLOCK_BIG
 #define REXSIM_BLOCK_BIG 256
-#endif
-// fast-path PGS formulation: 1 = pre-scaled row sums + lane-local residual (no per-iteration reduction), 0 = the round-1 form
-#ifndef REXSIM_PGS_FAST
-#define REXSIM_PGS_FAST 1
 #endif
 // resident CTAs per SM of the large-batch build (register cap 65536 / (128 * REXSIM_OCC_BIG))
 #ifndef REXSIM_OCC_BIG
@@ -597,7 +594,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     const bool activeU = bestU <= brk;
     const bool activeB = (leg == 0) && (bestB <= brk);
     // joint limits (btMultiBodyJointLimitConstraint: a row only while the limit is violated); one row per leg is modelled
-    int limJ = -1; float limSg = 0.f, limPen = 0.f;
+    int limJ = -1; float limSg = 0.f, limPen = 0.f; int nviolL = 0;
     {
         int nviol = 0;
 #pragma unroll
@@ -607,6 +604,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             if (L.q[j] - lo <= 0.f) { limJ = j; limSg = 1.f; limPen = L.q[j] - lo; nviol++; }
         }
         if (nviol > 1) L.err |= REXSIM_FLAG_JOINT_LIMIT;      // more than one violated limit in a leg: not modelled
+        nviolL = nviol;
     }
     L.contact = (active ? 1 : 0) | (activeU ? 2 : 0) | (activeB ? 4 : 0);
     // arm joint limits (lane 0): bit j set when joint j is outside [lower, upper]; sign +1 lower / -1 upper
@@ -623,7 +621,11 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             }
         }
     }
-    const unsigned envf = or4((active ? 1u : 0u) | ((activeU || activeB || limJ >= 0 || armLim) ? 2u : 0u));
+    // bit 0: a foot contact; bit 1: rows only the generic path solves (body contacts, two violated limits in one leg, more than
+    // ARM_KA arm limits); bit 2: arm joint limits, bit 3: a leg joint limit -- both ride along in the fast path
+    const int nArmLim = ARM ? __popc(armLim) : 0;
+    const unsigned envf = or4((active ? 1u : 0u) | ((activeU || activeB || nviolL > 1 || nArmLim > ARM_KA) ? 2u : 0u) |
+                              (nArmLim ? 4u : 0u) | (limJ >= 0 ? 8u : 0u));
     float dqA[ARM_NJ];
     if (ARM) {
 #pragma unroll
@@ -632,8 +634,15 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     float dq1 = 0.f, dq2 = 0.f, dq3 = 0.f; SV dv0; dv0.a = mk(0, 0, 0); dv0.l = mk(0, 0, 0);
     const float mu = P.cfg.friction, thr = P.cfg.residual_threshold;
     const int iters = P.cfg.solver_iterations;
-    if (envf == 1u) {
-        // ================= fast path: toe / foot contacts only =============================================
+    // ================= fast path: foot contacts (+ one joint-limit row per leg, + up to ARM_KA arm limit rows) ===========
+    // Compiled twice: LIM = false is the lean form every walking / galloping sub-step takes (12 rows); LIM = true adds the
+    // leg's joint-limit row as a fourth row of each lane (standing up from the folded rest pose: every such sub-step).
+    auto fast_path = [&](auto lim_tag) {
+        constexpr bool LIM = decltype(lim_tag)::value;
+        constexpr int CL = 12;                                  // first leg-limit column
+        constexpr int CA = 12 + (LIM ? 4 : 0);                  // first arm-limit column
+        constexpr int NC = CA + (ARM ? ARM_KA : 0);
+        constexpr int NR = LIM ? 4 : 3;                         // own rows: n, t1, t2 (, limit)
         // ---- constraint rows of the own contact: n, t1, t2 ----------------------------------------------
         V3 t1, t2;
         if (TERRAIN == REXSIM_TERRAIN_PLANE) { t1 = mk(0.f, -1.f, 0.f); t2 = mk(1.f, 0.f, 0.f); }
@@ -645,8 +654,9 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         SV v3s = sfma(qs3, S3v, sfma(qs2, S2, sfma(qs1, S1, vs)));   // foot spatial velocity after the free update
         float relv[3] = {sdot(F[0], v3s), sdot(F[1], v3s), sdot(F[2], v3s)};
         // unit impulse responses of the own rows: inward along the leg gives the base bias g_d, then the base solve
-        float uD1[3], uD2[3], uD3[3]; SV g[3], dvb[3];
+        float uD1[NR], uD2[NR], uD3[NR]; SV g[NR], dvb[NR];
         float Dd[3][3];                // own-leg response with the base held fixed: Dd[r][d] = F_r . w_d
+        float eeF[LIM ? 3 : 1];        // joint-rate response of the LIMITED joint to each foot row (fixed base): the limit row's own terms
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             SV pD; pD.a = mk(-F[d].a.x, -F[d].a.y, -F[d].a.z); pD.l = mk(-F[d].l.x, -F[d].l.y, -F[d].l.z);
@@ -655,27 +665,115 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             uD1[d] = -sdot(S1, pD); pD = sfma(uD1[d] * k1, U1, pD);
             g[d] = pD;
             dvb[d] = neg_mul(Minv, pD);
-            SV w = (uD1[d] * k1) * S1;
-            float e2 = (uD2[d] - sdot(U2, w)) * k2; w = sfma(e2, S2, w);
-            float e3 = (uD3[d] - sdot(U3, w)) * k3; w = sfma(e3, S3v, w);
+            const float e1 = uD1[d] * k1;
+            SV w = e1 * S1;
+            const float e2 = (uD2[d] - sdot(U2, w)) * k2; w = sfma(e2, S2, w);
+            const float e3 = (uD3[d] - sdot(U3, w)) * k3; w = sfma(e3, S3v, w);
             Dd[0][d] = sdot(F[0], w); Dd[1][d] = sdot(F[1], w); Dd[2][d] = sdot(F[2], w);
+            if (LIM) eeF[d] = limJ == 0 ? e1 : (limJ == 1 ? e2 : e3);
         }
-        // Delassus rows A[r][3*s+d] = J_r M^-1 J_(s,d)^T.  The response of the own foot to a base velocity change b
-        // is T b with T = prod(I - S_i k_i U_i^T), and T^T F_r = -g_r is already known from the inward pass, so a
-        // foreign column costs one 6-dot; own columns add the fixed-base term Dd.
-        float A[3][12];
+        // the own joint-limit row (btMultiBodyJointLimitConstraint): unit generalized force limSg on joint limJ
+        float denL = 1.f, rhsL = 0.f, ownLL = 0.f;
+        const bool hasL = LIM && limJ >= 0;
+        if (LIM) {
+            const float j0 = limJ == 0 ? limSg : 0.f, j1 = limJ == 1 ? limSg : 0.f, j2 = limJ == 2 ? limSg : 0.f;
+            const float u3 = j2; SV pD = (u3 * k3) * U3;
+            const float u2 = j1 - sdot(S2, pD); pD = sfma(u2 * k2, U2, pD);
+            const float u1 = j0 - sdot(S1, pD); pD = sfma(u1 * k1, U1, pD);
+            uD1[3] = u1; uD2[3] = u2; uD3[3] = u3;
+            g[3] = pD; dvb[3] = neg_mul(Minv, pD);
+            const float e1 = u1 * k1; SV w = e1 * S1;
+            const float e2 = (u2 - sdot(U2, w)) * k2; w = sfma(e2, S2, w);
+            const float e3 = (u3 - sdot(U3, w)) * k3;
+            ownLL = j0 * e1 + j1 * e2 + j2 * e3;
+            denL = hasL ? ownLL - sdot(g[3], dvb[3]) : 1.f;
+            const float relL = j0 * qs1 + j1 * qs2 + j2 * qs3;
+            // m_splitImpulse: beyond the -0.04 threshold the positional term goes to m_rhsPenetration, which is never applied
+            rhsL = hasL ? ((limPen > -0.04f) ? (-limPen * P.cfg.erp_joint * inv_dt - relL) : -relL) / denL : 0.f;
+        }
+        // ARM builds: up to ARM_KA violated arm joint limits ride along as extra rows owned by lane 0 (slot a = a-th violated
+        // joint, ascending); the rest pose of the arm keeps three of them active all the time (rexsim_arm.cuh)
+        float A[NR][NC];
+        float Aarm[ARM ? ARM_KA : 1][NC];          // rows of the arm slots (meaningful on lane 0, zero elsewhere)
+        SV gA[ARM ? ARM_KA : 1];
+        if (ARM) {
+#pragma unroll
+            for (int a = 0; a < ARM_KA; a++) { gA[a].a = mk(0.f, 0.f, 0.f); gA[a].l = mk(0.f, 0.f, 0.f); }
+        }
+        float rhsA[ARM ? ARM_KA : 1], denA[ARM ? ARM_KA : 1], dinvA[ARM ? ARM_KA : 1], sgA[ARM ? ARM_KA : 1];
+        float uuA[ARM ? ARM_KA : 1][ARM_NJ];       // inward joint terms of each slot (lane 0; applied at the end)
+        SV bbA[ARM ? ARM_KA : 1];
+        bool actA[ARM ? ARM_KA : 1];
+        if (ARM) {
+            float eeA[ARM_KA][ARM_NJ]; int jA[ARM_KA];
+            unsigned rem = armLim;
+#pragma unroll
+            for (int a = 0; a < ARM_KA; a++) {
+                actA[a] = rem != 0u;
+                const int j = actA[a] ? __ffs(rem) - 1 : 0;
+                rem &= rem - 1u;
+                jA[a] = j; sgA[a] = 0.f; rhsA[a] = 0.f; denA[a] = 1.f; dinvA[a] = 0.f;
+                bbA[a].a = mk(0.f, 0.f, 0.f); bbA[a].l = mk(0.f, 0.f, 0.f);
+#pragma unroll
+                for (int cc = 0; cc < ARM_NJ; cc++) { eeA[a][cc] = 0.f; uuA[a][cc] = 0.f; }
+                if (actA[a]) {               // lane 0 only (armLim is zero on the other lanes)
+                    const float sg = armSg[j];
+                    arm_row(AR, j, sg, gA[a], eeA[a], uuA[a]);
+                    bbA[a] = neg_mul(Minv, gA[a]);
+                    sgA[a] = sg;
+                    denA[a] = -sdot(gA[a], bbA[a]) + sg * eeA[a][j];
+                    dinvA[a] = 1.0f / denA[a];
+                    const float relvA = sg * AR.qs[j];
+                    rhsA[a] = (armPen[j] > -0.04f) ? (-armPen[j] * P.cfg.erp_joint * inv_dt - relvA) * dinvA[a] : -relvA * dinvA[a];
+                }
+            }
+            // arm x arm block: velocity of slot a's joint per unit impulse of slot c = sg_a * ee_c[j_a] - g_a . b_c
+#pragma unroll
+            for (int a = 0; a < ARM_KA; a++)
+#pragma unroll
+                for (int cc = 0; cc < ARM_KA; cc++)
+                    Aarm[a][CA + cc] = (actA[a] && actA[cc]) ? sgA[a] * eeA[cc][jA[a]] - sdot(gA[a], bbA[cc]) : 0.f;
+            // every lane needs the arm slots' base responses for its own rows' arm columns, and the slots' status
+#pragma unroll
+            for (int a = 0; a < ARM_KA; a++) {
+                bbA[a] = bcast4(bbA[a], 0);
+                actA[a] = __shfl_sync(env_mask(), actA[a] ? 1 : 0, 0, 4) != 0;
+                denA[a] = bcast4(denA[a], 0);
+#pragma unroll
+                for (int r = 0; r < NR; r++) A[r][CA + a] = -sdot(g[r], bbA[a]);
+            }
+        }
+        // Delassus rows A[r][c] = J_r M^-1 J_c^T.  The response of the own foot to a base velocity change b is T b with
+        // T = prod(I - S_i k_i U_i^T), and T^T F_r = -g_r is already known from the inward pass, so a foreign column costs one
+        // 6-dot; own columns add the fixed-base term (Dd between foot rows; the limited joint's rate eeF between foot and limit row).
 #pragma unroll
         for (int s = 0; s < 4; s++) {
+            const bool own = (s == leg);
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 SV b = bcast4(dvb[d], s);
-                const bool own = (s == leg);
 #pragma unroll
                 for (int r = 0; r < 3; r++) A[r][3 * s + d] = (own ? Dd[r][d] : 0.f) - sdot(g[r], b);
+                if (LIM) A[3][3 * s + d] = (own ? limSg * eeF[d] : 0.f) - sdot(g[3], b);
+                if (ARM) {
+#pragma unroll
+                    for (int a = 0; a < ARM_KA; a++) Aarm[a][3 * s + d] = -sdot(gA[a], b);
+                }
+            }
+            if (LIM) {
+                SV b = bcast4(dvb[3], s);           // zero response when lane s has no violated limit
+                const bool sl = __shfl_sync(env_mask(), hasL ? 1 : 0, s, 4) != 0;
+#pragma unroll
+                for (int r = 0; r < 3; r++) A[r][CL + s] = sl ? (own ? limSg * eeF[r] : 0.f) - sdot(g[r], b) : 0.f;
+                A[3][CL + s] = sl ? (own ? ownLL : 0.f) - sdot(g[3], b) : 0.f;
+                if (ARM) {
+#pragma unroll
+                    for (int a = 0; a < ARM_KA; a++) Aarm[a][CL + s] = sl ? -sdot(gA[a], b) : 0.f;
+                }
             }
         }
         // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
-        float den[3], dinv[3], rhs[3];
+        float den[NR], dinv[NR], rhs[NR];
 #pragma unroll
         for (int d = 0; d < 3; d++) { den[d] = Dd[d][d] - sdot(g[d], dvb[d]); dinv[d] = 1.0f / den[d]; }
         {
@@ -687,30 +785,75 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             rhs[1] = -relv[1] * dinv[1];
             rhs[2] = -relv[2] * dinv[2];
         }
-        // ---- PGS in impulse space, Bullet row order: normals 0..3, then (t1,t2) of contacts 0..3 -----------
-        // Each lane keeps only its own three impulses and the running row sums rs[d] = sum_j A[d][j] lambda_j;
-        // the owner of a row broadcasts its impulse CHANGE and every lane folds it into its sums (3 FMA).
-        float lam[3] = {0.f, 0.f, 0.f};
+        if (LIM) { den[3] = denL; dinv[3] = 1.0f / denL; rhs[3] = rhsL; }
+        // ---- PGS in impulse space, Bullet row order: joint-limit rows (legs, arm), normals 0..3, then (t1,t2) of contacts 0..3 ----
+        // Each lane keeps only its own impulses and the PRE-SCALED running row sums t[d] = rhs[d] - dinv[d] * sum_j A[d][j] lambda_j:
+        // t[d] IS the next impulse change of row d, so the serial chain per row is clamp -> shuffle -> one FMA.  The owner of a
+        // row broadcasts its impulse CHANGE and every lane folds it into its sums.  Every lane sees every change, so with the row
+        // denominators replicated once per sub-step each lane evaluates the iteration's residual itself: no reduction (two
+        // dependent shuffles) at the end of every iteration.  Same max, same early-out decision on all lanes of the env.
+        float lam[NR];
+        float t[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            lam[r] = 0.f; t[r] = rhs[r];
+#pragma unroll
+            for (int cc = 0; cc < NC; cc++) A[r][cc] *= -dinv[r];
+        }
         bool running = true;             // env-uniform: the 4 lanes of an env leave the loop together
         const bool mine = active;
-#if REXSIM_PGS_FAST
-        // Row sums are kept pre-scaled: t[d] = rhs[d] - dinv[d] * sum_j A[d][j] lambda_j IS the next impulse change of row d, so
-        // the serial chain per row is clamp -> shuffle -> one FMA.  Every lane sees every impulse change (the broadcast), so
-        // with the 12 row denominators replicated once per sub-step each lane evaluates the iteration's residual itself:
-        // no reduction (two dependent shuffles) at the end of every iteration.  Same max, same early-out decision on all lanes.
-        float t[3] = {rhs[0], rhs[1], rhs[2]};
+        float tA[ARM ? ARM_KA : 1], lamA[ARM ? ARM_KA : 1];
+        if (ARM) {
 #pragma unroll
-        for (int r = 0; r < 3; r++)
+            for (int a = 0; a < ARM_KA; a++) {
+                tA[a] = rhsA[a]; lamA[a] = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < 12; cc++) A[r][cc] *= -dinv[r];
-        float denAll[4][3];
+                for (int cc = 0; cc < NC; cc++) Aarm[a][cc] *= -dinvA[a];
+            }
+        }
+        float denAll[4][NR];
 #pragma unroll
         for (int s = 0; s < 4; s++)
 #pragma unroll
-            for (int d = 0; d < 3; d++) denAll[s][d] = bcast4(den[d], s);
+            for (int d = 0; d < NR; d++) denAll[s][d] = bcast4(den[d], s);
         for (int it = 0; it < iters && running; it++) {
             L.cost++;
             float resid = 0.f;
+            // joint-limit rows first, in joint order (4 legs, then the arm), the direction alternating per iteration
+            // (btMultiBodyConstraintSolver::solveSingleIteration): even iterations descending, odd ascending
+            auto arm_round = [&](const int a) {
+                float dI = tA[a];
+                if (lamA[a] + dI < 0.f) dI = -lamA[a];
+                dI = (actA[a] && leg == 0) ? dI : 0.f;
+                lamA[a] += dI;
+                const float dl = bcast4(dI, 0);
+                const float rr = dl * denA[a]; resid = fmaxf(resid, rr * rr);
+#pragma unroll
+                for (int r = 0; r < NR; r++) t[r] = fmaf(A[r][CA + a], dl, t[r]);
+#pragma unroll
+                for (int c2 = 0; c2 < ARM_KA; c2++) tA[c2] = fmaf(Aarm[c2][CA + a], dl, tA[c2]);
+            };
+            auto leg_round = [&](const int s) {
+                float dI = t[NR - 1];
+                if (lam[NR - 1] + dI < 0.f) dI = -lam[NR - 1];
+                dI = (hasL && leg == s) ? dI : 0.f;
+                lam[NR - 1] += dI;
+                const float dl = bcast4(dI, s);
+                const float rr = dl * denAll[s][NR - 1]; resid = fmaxf(resid, rr * rr);
+#pragma unroll
+                for (int r = 0; r < NR; r++) t[r] = fmaf(A[r][CL + s], dl, t[r]);
+                if (ARM) {
+#pragma unroll
+                    for (int a = 0; a < ARM_KA; a++) tA[a] = fmaf(Aarm[a][CL + s], dl, tA[a]);
+                }
+            };
+            if (it & 1) {
+                if (LIM) { leg_round(0); leg_round(1); leg_round(2); leg_round(3); }
+                if (ARM) { arm_round(0); arm_round(1); arm_round(2); }
+            } else {
+                if (ARM) { arm_round(2); arm_round(1); arm_round(0); }
+                if (LIM) { leg_round(3); leg_round(2); leg_round(1); leg_round(0); }
+            }
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 float dI = t[0];
@@ -720,10 +863,17 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 lam[0] += dI;
                 const float dl = bcast4(dI, s);
                 const float rr = dl * denAll[s][0]; resid = fmaxf(resid, rr * rr);
-                t[0] = fmaf(A[0][3 * s], dl, t[0]); t[1] = fmaf(A[1][3 * s], dl, t[1]); t[2] = fmaf(A[2][3 * s], dl, t[2]);
+#pragma unroll
+                for (int r = 0; r < NR; r++) t[r] = fmaf(A[r][3 * s], dl, t[r]);
+                if (ARM) {
+#pragma unroll
+                    for (int a = 0; a < ARM_KA; a++) tA[a] = fmaf(Aarm[a][3 * s], dl, tA[a]);
+                }
             }
 #pragma unroll
             for (int s = 0; s < 4; s++) {
+                // both friction rows of contact s belong to lane s: update t1, fold its change into the own t2 sum
+                // locally, update t2, then broadcast the two changes together (one communication round per contact)
                 const float lim = mu * lam[0];
                 const bool upd = mine && (leg == s) && (lam[0] > 0.f);
                 float dI1 = t[1];
@@ -739,68 +889,46 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 const float dl1 = bcast4(dI1, s), dl2 = bcast4(dI2, s);
                 const float r1 = dl1 * denAll[s][1], r2 = dl2 * denAll[s][2];
                 resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
-                t[0] = fmaf(A[0][3 * s + 2], dl2, fmaf(A[0][3 * s + 1], dl1, t[0]));
-                t[1] = fmaf(A[1][3 * s + 2], dl2, fmaf(A[1][3 * s + 1], dl1, t[1]));
-                t[2] = fmaf(A[2][3 * s + 2], dl2, fmaf(A[2][3 * s + 1], dl1, t[2]));
+#pragma unroll
+                for (int r = 0; r < NR; r++) t[r] = fmaf(A[r][3 * s + 2], dl2, fmaf(A[r][3 * s + 1], dl1, t[r]));
+                if (ARM) {
+#pragma unroll
+                    for (int a = 0; a < ARM_KA; a++) tA[a] = fmaf(Aarm[a][3 * s + 2], dl2, fmaf(Aarm[a][3 * s + 1], dl1, tA[a]));
+                }
             }
             if (resid <= thr) running = false;
         }
-#else
-        float rs[3] = {0.f, 0.f, 0.f};
-        for (int it = 0; it < iters && running; it++) {
-            L.cost++;
-            float resid = 0.f;
+        // ---- apply the net impulse: one more response pass ---------------------------------------------------
+        float e1 = 0.f, e2 = 0.f, e3 = 0.f;
+        SV own_b; own_b.a = mk(0.f, 0.f, 0.f); own_b.l = mk(0.f, 0.f, 0.f);
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                float dI = rhs[0] - rs[0] * dinv[0];
-                if (lam[0] + dI < 0.f) dI = -lam[0];
-                const bool upd = mine && running && (leg == s);
-                dI = upd ? dI : 0.f;
-                lam[0] += dI;
-                float rr = dI * den[0]; resid = fmaxf(resid, rr * rr);
-                float dl = bcast4(dI, s);
-                rs[0] = fmaf(A[0][3 * s], dl, rs[0]); rs[1] = fmaf(A[1][3 * s], dl, rs[1]); rs[2] = fmaf(A[2][3 * s], dl, rs[2]);
-            }
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                // both friction rows of contact s belong to lane s: update t1, fold its change into the own t2 sum
-                // locally, update t2, then broadcast the two changes together (one communication round per contact)
-                const float lim = mu * lam[0];
-                const bool upd = mine && running && (leg == s) && (lam[0] > 0.f);
-                float dI1 = rhs[1] - rs[1] * dinv[1];
-                float sum1 = lam[1] + dI1;
-                if (sum1 < -lim) dI1 = -lim - lam[1]; else if (sum1 > lim) dI1 = lim - lam[1];
-                dI1 = upd ? dI1 : 0.f;
-                lam[1] += dI1;
-                float rs2 = fmaf(A[2][3 * s + 1], dI1, rs[2]);          // own lane: column 3*leg+1 == 3*s+1 when upd
-                float dI2 = rhs[2] - rs2 * dinv[2];
-                float sum2 = lam[2] + dI2;
-                if (sum2 < -lim) dI2 = -lim - lam[2]; else if (sum2 > lim) dI2 = lim - lam[2];
-                dI2 = upd ? dI2 : 0.f;
-                lam[2] += dI2;
-                float r1 = dI1 * den[1], r2 = dI2 * den[2];
-                resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
-                float dl1 = bcast4(dI1, s), dl2 = bcast4(dI2, s);
-                rs[0] = fmaf(A[0][3 * s + 2], dl2, fmaf(A[0][3 * s + 1], dl1, rs[0]));
-                rs[1] = fmaf(A[1][3 * s + 2], dl2, fmaf(A[1][3 * s + 1], dl1, rs[1]));
-                rs[2] = fmaf(A[2][3 * s + 2], dl2, fmaf(A[2][3 * s + 1], dl1, rs[2]));
-            }
-            resid = max4(resid);
-            if (resid <= thr) running = false;
+        for (int r = 0; r < NR; r++) {
+            e1 = fmaf(lam[r], uD1[r], e1); e2 = fmaf(lam[r], uD2[r], e2); e3 = fmaf(lam[r], uD3[r], e3);
+            own_b = sfma(lam[r], dvb[r], own_b);
         }
-#endif
-        // ---- apply the net contact impulse: one more response pass -----------------------------------------
-        const float ln = lam[0], l1 = lam[1], l2 = lam[2];
-        float e1 = ln * uD1[0] + l1 * uD1[1] + l2 * uD1[2];
-        float e2 = ln * uD2[0] + l1 * uD2[1] + l2 * uD2[2];
-        float e3 = ln * uD3[0] + l1 * uD3[1] + l2 * uD3[2];
-        SV own_b = sfma(ln, dvb[0], sfma(l1, dvb[1], l2 * dvb[2]));
+        float usA[ARM_NJ];
+        if (ARM) {
+#pragma unroll
+            for (int cc = 0; cc < ARM_NJ; cc++) usA[cc] = 0.f;
+            if (leg == 0) {
+#pragma unroll
+                for (int a = 0; a < ARM_KA; a++) {
+                    own_b = sfma(lamA[a], bbA[a], own_b);          // lamA is zero for inactive slots
+#pragma unroll
+                    for (int cc = 0; cc < ARM_NJ; cc++) usA[cc] = fmaf(lamA[a], uuA[a][cc], usA[cc]);
+                }
+            }
+        }
         dv0 = sum4(own_b);
         SV b = dv0;
         dq1 = (e1 - sdot(U1, b)) * k1; b = sfma(dq1, S1, b);
         dq2 = (e2 - sdot(U2, b)) * k2; b = sfma(dq2, S2, b);
         dq3 = (e3 - sdot(U3, b)) * k3;
-        if (ARM && leg == 0) { float z6[ARM_NJ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; arm_apply(AR, dv0, z6, dqA); }
+        if (ARM && leg == 0) arm_apply(AR, dv0, usA, dqA);
+    };
+    if (envf != 0u && !(envf & 2u)) {
+        if (envf & 8u) fast_path(std::true_type{});
+        else fast_path(std::false_type{});
     }
     else if (envf & 2u) {
         L.cost += 64;      // the generic path is several times the fast path: such envs sort together (rexsim_rebalance)

@@ -105,7 +105,12 @@ def test_reset_settle_and_draws(task, sig, kw):
         tq, tp = 3e-2, 2e-3      # + three arm limit rows permanently active and the solver at its cap: the fold-down is chaotic
     assert np.abs(sg["q"] - so["q"]).max() < tq and np.abs(sg["pos"] - so["pos"]).max() < tp
     assert np.abs(sg["quat"] - so["quat"]).max() < tq
-    np.testing.assert_allclose(og, oc, atol=10 * tq)
+    np.testing.assert_allclose(og[:, :2], oc[:, :2], atol=10 * tq)
+    # base rates at the end of the hold: with the arm's three limit rows pressed by their motors they are only as exact as the
+    # solver's 1e-7 early-out (fp64 oracle: -3.3e-3 rad/s at 1e-7, -3e-4 at 1e-9; fp32 oracle -2.8e-3)
+    np.testing.assert_allclose(og[:, 2:4], oc[:, 2:4], atol=1e-2 if kw.get("mark") == "arm" else 10 * tq)
+    if og.shape[1] > 4:
+        np.testing.assert_allclose(og[:, 4:], oc[:, 4:], atol=10 * tq)
     sf, si = env._state_f.cpu().numpy(), env._state_i.cpu().numpy()
     tp = np.array([ora.env(i).target_value if task == "poses" else ora.env(i).target_position for i in range(n)], np.float32)
     np.testing.assert_array_equal(sf[38], tp)                                         # F_TARGET
