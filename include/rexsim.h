@@ -50,7 +50,7 @@ enum { REXSIM_TERRAIN_PLANE = 0, REXSIM_TERRAIN_RANDOM = 1 };
 /* per-env device error bits (rexsim_step ORs them into err_flags[env]) */
 enum {
     REXSIM_FLAG_NONFINITE = 1,        /* non-finite state/obs/reward (ConvertTo32Bit raises, wrappers.py:522,542) */
-    REXSIM_FLAG_JOINT_LIMIT = 2,      /* more than one joint limit violated in one leg: only one limit row per leg is modelled */
+    REXSIM_FLAG_JOINT_LIMIT = 2,      /* reserved (every violated joint limit has its own row since round 2) */
     REXSIM_FLAG_BODY_CONTACT = 4,     /* reserved (body contacts are solved since the generic row path exists) */
     REXSIM_FLAG_TILE_MISS = 8,        /* a contact query fell outside the 0.8 m heightfield window staged in shared memory */
     REXSIM_FLAG_BAD_INDEX = 16,       /* rexsim_reset saw an index outside [0, N): skipped (aggregate word only) */

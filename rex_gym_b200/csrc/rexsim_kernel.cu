@@ -292,9 +292,9 @@ __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {   // btPlaneSp
     }
 }
 
-// generic-path Gauss-Seidel order after the 4 limit rows: normals (base, then per leg upper, foot), then frictions
+// generic-path Gauss-Seidel order after the limit rows (rows 0..2 of a lane = its three joint limits): normals (base, then per leg upper, foot), then frictions
 static __constant__ int c_seq_owner[27] = {0, 0, 0, 1, 1, 2, 2, 3, 3, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3};
-static __constant__ int c_seq_row[27] = {1, 4, 7, 4, 7, 4, 7, 4, 7, 2, 3, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9, 5, 6, 8, 9};
+static __constant__ int c_seq_row[27] = {3, 6, 9, 6, 9, 6, 9, 6, 9, 4, 5, 7, 8, 10, 11, 7, 8, 10, 11, 7, 8, 10, 11, 7, 8, 10, 11};
 
 // motor model + overheat (rex_gym/model/motor.py:76-143, rex_gym/model/rex.py:601-623) for one joint
 // q, qd: what the PD loop sees (pd_latency ago, rex.py:755-759); qd_true: the motor's actual rate (back-EMF, motor.py:131)
@@ -593,18 +593,18 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
     const bool active = best <= brk;
     const bool activeU = bestU <= brk;
     const bool activeB = (leg == 0) && (bestB <= brk);
-    // joint limits (btMultiBodyJointLimitConstraint: a row only while the limit is violated); one row per leg is modelled
+    // joint limits (btMultiBodyJointLimitConstraint: a row only while the limit is violated).  One violated limit in the leg
+    // rides in the fast solver path (limJ / limSg / limPen); two or three go to the generic path, one row per joint.
     int limJ = -1; float limSg = 0.f, limPen = 0.f; int nviolL = 0;
+    float limSgJ[3], limPenJ[3];
     {
-        int nviol = 0;
 #pragma unroll
         for (int j = 2; j >= 0; j--) {
             const float lo = LB[16 * j + 7], hi = LB[16 * j + 14];
-            if (hi - L.q[j] <= 0.f) { limJ = j; limSg = -1.f; limPen = hi - L.q[j]; nviol++; }
-            if (L.q[j] - lo <= 0.f) { limJ = j; limSg = 1.f; limPen = L.q[j] - lo; nviol++; }
+            limSgJ[j] = 0.f; limPenJ[j] = 0.f;
+            if (hi - L.q[j] <= 0.f) { limJ = j; limSg = -1.f; limPen = hi - L.q[j]; nviolL++; limSgJ[j] = -1.f; limPenJ[j] = limPen; }
+            if (L.q[j] - lo <= 0.f) { limJ = j; limSg = 1.f; limPen = L.q[j] - lo; nviolL++; limSgJ[j] = 1.f; limPenJ[j] = limPen; }
         }
-        if (nviol > 1) L.err |= REXSIM_FLAG_JOINT_LIMIT;      // more than one violated limit in a leg: not modelled
-        nviolL = nviol;
     }
     L.contact = (active ? 1 : 0) | (activeU ? 2 : 0) | (activeB ? 4 : 0);
     // arm joint limits (lane 0): bit j set when joint j is outside [lower, upper]; sign +1 lower / -1 upper
@@ -936,8 +936,8 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         // M^-1 of a star-shaped tree = per-leg block + a rank-6 coupling through the base, so no Delassus matrix is
         // needed: a row's velocity is  J_r dV = -g_r . beta + Jq_r . eps  with beta = base velocity change (replicated
         // on the 4 lanes) and eps = own-leg joint-rate change at fixed base.  Rows live in local memory (rare path).
-        // rows: 0 = joint limit | 1..3 base contact (lane 0) | 4..6 upper contact | 7..9 foot contact  (n, t1, t2)
-        constexpr int NR = 10;
+        // rows: 0..2 = joint limits of the own joints | 3..5 base contact (lane 0) | 6..8 upper contact | 9..11 foot contact  (n, t1, t2)
+        constexpr int NR = 12;
         float g_[NR][6], b_[NR][6], Jq_[NR][3], ee_[NR][3], uu_[NR][3], rhs_[NR], dinv_[NR], den_[NR], lam_[NR];
 #pragma unroll 1
         for (int r = 0; r < NR; r++) {
@@ -985,16 +985,20 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 } else rhs_[r0 + d] = -relv * dinv_[r0 + d];
             }
         };
-        if (limJ >= 0) {
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            const float sg = j == 0 ? limSgJ[0] : (j == 1 ? limSgJ[1] : limSgJ[2]);
+            if (sg == 0.f) continue;
+            const float pen = j == 0 ? limPenJ[0] : (j == 1 ? limPenJ[1] : limPenJ[2]);
             SV z; z.a = mk(0, 0, 0); z.l = mk(0, 0, 0);
-            float relv = setup_row(0, z, limJ == 0 ? limSg : 0.f, limJ == 1 ? limSg : 0.f, limJ == 2 ? limSg : 0.f);
+            float relv = setup_row(j, z, j == 0 ? sg : 0.f, j == 1 ? sg : 0.f, j == 2 ? sg : 0.f);
             // btMultiBodyJointLimitConstraint with m_splitImpulse: beyond the -0.04 threshold the positional term goes to
             // m_rhsPenetration, which the multibody solver never applies (the row only stops further motion)
-            rhs_[0] = (limPen > -0.04f) ? (-limPen * P.cfg.erp_joint * inv_dt - relv) * dinv_[0] : -relv * dinv_[0];
+            rhs_[j] = (pen > -0.04f) ? (-pen * P.cfg.erp_joint * inv_dt - relv) * dinv_[j] : -relv * dinv_[j];
         }
-        if (activeB) setup_contact(1, rcB, nrmB, 0, bestB);
-        if (activeU) setup_contact(4, rcU, nrmU, kU, bestU);
-        if (active) setup_contact(7, rc, nrm, 3, best);
+        if (activeB) setup_contact(3, rcB, nrmB, 0, bestB);
+        if (activeU) setup_contact(6, rcU, nrmU, kU, bestU);
+        if (active) setup_contact(9, rc, nrm, 3, best);
         // arm joint-limit rows (lane 0)
         float gA_[ARM ? ARM_NJ : 1][6], bA_[ARM ? ARM_NJ : 1][6], eeA_[ARM ? ARM_NJ : 1][ARM_NJ], uuA_[ARM ? ARM_NJ : 1][ARM_NJ];
         float rhsA_[ARM_NJ], dinvA_[ARM_NJ], denA_[ARM_NJ], lamA_[ARM_NJ], epsA[ARM_NJ], usA[ARM_NJ];
@@ -1017,7 +1021,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         SV beta; beta.a = mk(0, 0, 0); beta.l = mk(0, 0, 0);
         float eps0 = 0.f, eps1 = 0.f, eps2 = 0.f, us0 = 0.f, us1 = 0.f, us2 = 0.f;
         // compact the Gauss-Seidel sequence to the rows that exist in this env (env-uniform: built from shuffled bits)
-        constexpr int NLIM = ARM ? 4 + ARM_NJ : 4;       // limit rows in joint order: 4 leg rows (one per lane), then the arm
+        constexpr int NLIM = ARM ? 12 + ARM_NJ : 12;     // limit rows in joint order: 3 per leg (lane), then the arm
         unsigned char llist[NLIM], clist[27];
         int nl = 0, nc = 0;
         {
@@ -1027,7 +1031,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
             const unsigned armAll = ARM ? __shfl_sync(env_mask(), armLim, 0, 4) : 0u;
 #pragma unroll
             for (int idx = 0; idx < NLIM; idx++) {
-                const bool a = idx < 4 ? (actAll[idx < 4 ? idx : 0] & 1u) : ((armAll >> (idx - 4)) & 1u);
+                const bool a = idx < 12 ? ((actAll[idx < 12 ? idx / 3 : 0] >> (idx % 3)) & 1u) : ((armAll >> (idx - 12)) & 1u);
                 if (a) llist[nl++] = (unsigned char)idx;
             }
 #pragma unroll 1
@@ -1046,8 +1050,8 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                 int o, ri;
                 if (tt < nl) {                                      // limit rows: direction alternates per iteration
                     const int idx = llist[(it & 1) ? tt : nl - 1 - tt];
-                    if (ARM && idx >= 4) {                          // an arm joint-limit row, owned by lane 0
-                        const int j = idx - 4;
+                    if (ARM && idx >= 12) {                         // an arm joint-limit row, owned by lane 0
+                        const int j = idx - 12;
                         float rsumA = armSg[j] * epsA[j] - (gA_[j][0] * beta.a.x + gA_[j][1] * beta.a.y + gA_[j][2] * beta.a.z + gA_[j][3] * beta.l.x + gA_[j][4] * beta.l.y + gA_[j][5] * beta.l.z);
                         float dIA = rhsA_[j] - rsumA * dinvA_[j];
                         if (lamA_[j] + dIA < 0.f) dIA = -lamA_[j];
@@ -1060,10 +1064,10 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
                         beta = beta + bcast4(dBA, 0);
                         continue;
                     }
-                    o = idx; ri = 0;
+                    o = idx / 3; ri = idx % 3;
                 }
                 else { const int t = clist[tt - nl]; o = c_seq_owner[t]; ri = c_seq_row[t]; }
-                const int ph = (ri == 0) ? 0 : (ri - 1) % 3;            // 0: unilateral row, 1/2: friction row
+                const int ph = (ri < 3) ? 0 : ri % 3;                   // 0: unilateral row (limit / normal), 1/2: friction row
                 float rsum = Jq_[ri][0] * eps0 + Jq_[ri][1] * eps1 + Jq_[ri][2] * eps2
                            - (g_[ri][0] * beta.a.x + g_[ri][1] * beta.a.y + g_[ri][2] * beta.a.z + g_[ri][3] * beta.l.x + g_[ri][4] * beta.l.y + g_[ri][5] * beta.l.z);
                 float dI = rhs_[ri] - rsum * dinv_[ri];

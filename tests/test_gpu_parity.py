@@ -262,6 +262,48 @@ def test_one_step_is_tight(task, sig, kw, bound):
     env.close()
 
 
+@pytest.mark.parametrize("in_air", [True, False])
+def test_several_joint_limits_in_one_leg(in_air):
+    """btMultiBodyJointLimitConstraint adds one row per VIOLATED limit; a leg with two or three of them (round 1 flagged that
+    case instead of solving it) takes the generic solver path with one row per joint, a single one rides in the fast path.
+    Both legs of the batch are pushed past two / three limits at once, in the air (limit rows only) and standing (with the
+    foot contacts), and one control step is compared with the oracle."""
+    n = 32
+    kw = dict(target_position=2.0, backwards=False)
+    env, ora = _env("walk", n, **kw), _oracle("walk", n, **kw)
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(3)
+    so = _oracle_state(ora, n)
+    q, qd, pos = so["q"].copy(), so["qd"].copy(), so["pos"].copy()
+    for i in range(n):
+        legs = rng.choice(4, size=1 + i % 3, replace=False)
+        for l in legs:
+            nv = 2 + (i + l) % 2                      # two or three violated limits in this leg
+            q[i, 3 * l + 1] = 0.97 + rng.uniform(0.002, 0.03)          # leg joint beyond its upper limit (rex.urdf)
+            q[i, 3 * l + 2] = -0.1 - rng.uniform(0.002, 0.03)          # foot joint beyond its lower limit
+            if nv == 3:
+                q[i, 3 * l] = (1.0 + rng.uniform(0.002, 0.03)) * (1 if l % 2 else -1)
+            qd[i, 3 * l:3 * l + 3] = rng.uniform(-1.0, 1.0, 3)
+        if in_air:
+            pos[i, 2] = 0.4
+    for i in range(n):                                 # the oracle has no set_state: write the struct
+        e = ora.env(i)
+        for j in range(12):
+            e.q[j], e.qd[j] = q[i, j], qd[i, j]
+        for a in range(3):
+            e.pos[a] = pos[i, a]
+    env.set_state(pos, so["quat"], so["linvel"], so["angvel"], q, qd)
+    a = np.zeros((n, 2), np.float32)
+    env.step(a); ora.step(a)
+    assert max(ora.env(i).limit_rows for i in range(n)) >= 0
+    sg, s2 = env.get_state(), _oracle_state(ora, n)
+    dq = np.abs(sg["q"] - s2["q"]).max(axis=1)
+    assert np.percentile(dq, 90) < 5e-5 and dq.max() < 3e-3, (np.percentile(dq, 90), dq.max())
+    assert np.abs(sg["pos"] - s2["pos"]).max() < 2e-4
+    assert (env.check_errors() & 3) == 0              # neither non-finite nor the (retired) joint-limit flag
+    env.close()
+
+
 def test_heightfield_contact_parity():
     n = 16
     kw = dict(signal_type="ik", terrain_type="random", num_fields=4, seed=9)
