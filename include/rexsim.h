@@ -94,7 +94,7 @@ typedef struct {
     float erp_contact, erp_joint;
     int32_t toe_npts;                 /* profile vertices of the toe prism in the model table */
     float toe_margin;                 /* added to the toe hull's reach [m]; -0.25 mm: identified on the recorded PyBullet touchdown */
-    float contact_breaking;           /* manifold breaking distance: a contact row exists while the distance is below it (0.64 mm) */
+    float contact_breaking;           /* manifold breaking distance: a contact row exists while the distance is below it (0.81 mm) */
     float link_damping;               /* btMultiBody m_linearDamping = m_angularDamping (0.04), applied to every link */
     float max_coordinate_velocity;    /* btMultiBody m_maxCoordinateVelocity (100): clamp on all generalised velocities */
     int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */

@@ -586,7 +586,7 @@ static void step_simulation(RexoSim* s, RexoEnv* e, const real* tau) {
     e->contact_mask = 0;
     /* contact exists while the distance is below the manifold's breaking threshold: btCollisionDispatcher::getNewManifold with
      * CD_USE_RELATIVE_CONTACT_BREAKING_THRESHOLD = min over the two shapes of getAngularMotionDisc() * gContactBreakingThreshold
-     * (0.02); for the toe link's compound shape that is 0.64 mm (rex_gym_b200/model_tables.py::contact_breaking_distance) */
+     * (0.02); for the toe link's compound shape that is 0.81 mm (rex_gym_b200/model_tables.py::contact_breaking_distance) */
     const real breaking = c->contact_breaking, slop = 1e-5;
     for (int sh = 0; sh < m->nshape; sh++) {    /* deepest sample point of each contact group vs ground */
         e->contact_vertex[sh] = -1;

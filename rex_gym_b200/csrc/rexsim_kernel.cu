@@ -588,7 +588,7 @@ __device__ __forceinline__ void physics_substep(const Params& P, const float* __
         }
     }
     // contact while the distance is below the manifold's breaking threshold (btCollisionDispatcher::getNewManifold, relative
-    // threshold: getAngularMotionDisc() * 0.02 of the toe link's shape = 0.64 mm; model_tables.contact_breaking_distance)
+    // threshold: getAngularMotionDisc() * 0.02 of the toe link's shape = 0.81 mm; model_tables.contact_breaking_distance)
     const float brk = P.cfg.contact_breaking;
     const bool active = best <= brk;
     const bool activeU = bestU <= brk;

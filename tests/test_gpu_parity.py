@@ -421,6 +421,52 @@ def test_full_size_properties_65536():
     big.close(); shard.close()
 
 
+@pytest.mark.parametrize("name,task,n,kw", [
+    ("C2", "walk", 65536, dict(signal_type="ik", target_position=2.0, backwards=False)),
+    ("C3", "gallop", 16384, dict(signal_type="ol", motor_kp_range=(0.8, 1.2), motor_kd_range=(0.01, 0.03))),
+    ("C4", "turn", 16384, dict(signal_type="ik", terrain_type="random", num_fields=64)),
+    ("C5", "standup", 16384, dict(signal_type="ol", mark="arm"))])
+def test_baseline_size_batches_against_the_oracle(name, task, n, kw):
+    """The BASELINE configurations at their per-GPU sizes, checked against the ORACLE (not only against themselves): a window
+    of 48 consecutive envs from the middle of the batch is re-simulated by the fp64 oracle with the same global env ids
+    (env_offset keys every reset draw) on the same actions.  Draws and episode bookkeeping bit-exact; observations / rewards within
+    the free-running tolerances over the first 40 control steps; the large batches run the 128-register 256-thread build."""
+    w0, nw, steps = n // 2 + 37, 48, 40
+    common = dict(normalize=True, seed=11)
+    env = _env(task, n, **common, **kw)
+    ora = _oracle(task, nw, env_offset=w0, **common, **kw)
+    og = env.reset()[w0:w0 + nw]
+    oc = ora.reset()
+    rough, arm = kw.get("terrain_type") == "random", kw.get("mark") == "arm"
+    np.testing.assert_allclose(og[:, :2], oc[:, :2], atol=2e-5 if not (rough or arm) else 2e-4)      # RangeNormalize'd roll / pitch
+    sf = env._state_f.cpu().numpy()[:, w0:w0 + nw]
+    np.testing.assert_array_equal(sf[38], np.array([ora.env(i).target_position for i in range(nw)], np.float32))
+    np.testing.assert_array_equal(sf[41], np.array([ora.env(i).kp for i in range(nw)], np.float32))
+    np.testing.assert_array_equal(sf[39], np.array([ora.env(i).target_orient for i in range(nw)], np.float32))
+    if arm:            # start both from the oracle's settled state (chaotic fold-down, see test_reset_settle_and_draws)
+        st = env.get_state()
+        so = _oracle_state(ora, nw)
+        for k in ("pos", "quat", "linvel", "angvel", "q", "qd"):
+            st[k][w0:w0 + nw] = so[k]
+        env.set_state(st["pos"], st["quat"], st["linvel"], st["angvel"], st["q"], st["qd"])
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    acts = torch.rand((steps, n, env.action_dim), device="cuda", generator=g) * 2 - 1
+    err = []
+    for k in range(steps):
+        o, r, d, _ = env.step(acts[k])
+        oc, rc, dc = ora.step(acts[k, w0:w0 + nw].cpu().numpy())
+        np.testing.assert_array_equal(d[w0:w0 + nw].cpu().numpy(), dc)
+        err.append(np.abs(o[w0:w0 + nw, :2].cpu().numpy() - oc[:, :2]).max(axis=1))
+        if not (rough or arm):
+            np.testing.assert_allclose(r[w0:w0 + nw].cpu().numpy(), rc, atol=5e-3)
+    err = np.concatenate(err) * (2 * np.pi + 0.01)                      # back to radians
+    tol = 5e-3 if (rough or arm) else 1e-3
+    # heightfield: one env of the window meets a block edge one sub-step apart (6e-3 rad for a few steps; p90 is 9e-5)
+    assert np.percentile(err, 90) < tol / 5 and err.max() < (2e-2 if rough else tol), (name, np.percentile(err, 90), err.max())
+    assert (env.check_errors() & 1) == 0
+    env.close()
+
+
 def test_single_env_facade_matches_the_reference_signatures():
     """gym.Env surface of the reference (rex_gym_env.py:296-414): reset() -> obs[O], step(a) -> 4-tuple with info['action']."""
     from rex_gym_b200.envs.gym.walk_env import RexWalkEnv

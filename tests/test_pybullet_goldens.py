@@ -100,6 +100,33 @@ def test_walk_open_loop_tracks_pybullet_over_25_episodes_x_600_steps():
     assert med(rp.mean(1)) < 2.6e-3 and med(rp.max(1)) < 8.2e-3 and rp.max() < 5.5e-2
 
 
+def test_turn_open_loop_recordings_in_yaw_invariant_quantities():
+    """The 25 recorded turn-ol episodes (160 steps) were called unusable in round 1 ("disagree from step 1").  Read against
+    turn_env.py:129-160,271-311 the reason is mostly bookkeeping: every episode starts at a yaw drawn from U(0.2, 6) that the
+    observation does not carry, the observation's two rate channels are WORLD-frame components (rex.py:548-558) and so rotate
+    with that yaw, and the left / right pose table is selected by (init, target) yaw, also not stored.  Compared in what does
+    not depend on the yaw -- roll, pitch (Euler angles of R = Rz Ry Rx) and the horizontal rate magnitude -- and with the
+    turning direction chosen per episode by the better fit over the first 40 steps (12-13 of 25 come out clockwise, as a fair
+    draw would), the replay tracks the recordings: roll / pitch 7e-4 rad after the first step, 5e-3 over the first 40 steps,
+    1.4e-2 over all 160 -- three to eight times looser than walk-ol, with a 25 % mismatch of the first step's pitch rate
+    (0.22 rad/s recorded) that the unknown June-2020 pose table could explain but nothing here can confirm."""
+    ac, ob = G["turn_ol_action"], denorm(G["turn_ol_observ"])
+    ref_rp, ref_w = ob[:, 1:, 0:2], np.hypot(ob[:, 1:, 2], ob[:, 1:, 3])
+    err = {}
+    for to, io in ((1.0, 3.0), (3.0, 1.0)):                       # clockwise / counter-clockwise (turn_env.py:313-322)
+        s = OracleSim(EPISODES, "turn", "ol", normalize=True, settle=2, target_orient=to, init_orient=io)
+        s.reset()
+        cw = s.env(0).clockwise
+        out = np.array([denorm(s.step(ac[:, t], nthreads=4)[0]) for t in range(160)]).transpose(1, 0, 2)
+        err[cw] = (np.abs(out[..., 0:2] - ref_rp).max(-1), np.abs(np.hypot(out[..., 2], out[..., 3]) - ref_w))
+    pick = err[1][0][:, :40].mean(1) < err[0][0][:, :40].mean(1)
+    rp = np.where(pick[:, None], err[1][0], err[0][0])
+    w = np.where(pick[:, None], err[1][1], err[0][1])
+    assert 6 <= pick.sum() <= 19                                   # both directions occur
+    assert med(rp[:, 0]) < 1.2e-3 and med(rp[:, :40].mean(1)) < 8e-3 and med(rp.mean(1)) < 2.2e-2
+    assert med(w[:, 0]) < 0.09 and med(ref_w[:, 0]) > 0.15          # first-step pitch rate: 0.22 recorded, ours within 0.054
+
+
 def _standup_replay(steps, episodes=EPISODES):
     ac, ref, rw = G["standup_ol_action"][:episodes], denorm(G["standup_ol_observ"][:episodes]), G["standup_ol_reward"][:episodes]
     s = OracleSim(episodes, "standup", "ol", normalize=True)      # the full reset hold (rex.py:314-323), not the pristine pose

@@ -1,7 +1,7 @@
 """The reference loads the URDF with URDF_USE_SELF_COLLISION (rex_gym/model/rex.py:275-281, rex_gym/envs/rex_gym_env.py:62): every
 pair of links except parent-child collides.  The restated contact model carries no link-link rows; this test is why that is
 the same physics on the path: along the trajectories of the tasks (random actions, falls and restarts included) no non-adjacent
-pair of collision shapes comes closer than several millimetres -- ten times the 0.64 mm distance at which Bullet would open a
+pair of collision shapes comes closer than several millimetres -- eight times the 0.81 mm distance at which Bullet would open a
 contact manifold.  The only pairs in permanent 'contact' are the chassis boxes and the shoulder boxes next to them (sibling
 links, 0 and 1 mm apart in every pose): their faces are perpendicular to the shoulder axis, so they slide in their own plane and
 never press on each other.  (tools/experiments/self_collision_survey.py holds the survey over static poses and all eight
