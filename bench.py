@@ -359,32 +359,37 @@ def main():
                    + ("" if world == 8 else f" (here {world} GPU(s) x {c5}" + (", no collective at 1 GPU)" if world == 1 else ")")))
         # the all-device rollout (policy inference + env step + filter update per control step,
         # one CUDA graph per 32-step window), same workload
-        try:
-            from rex_gym_b200.agents import ForwardGaussianPolicy, Rollout
-            envr = R.BatchedRexEnv(num_envs=n, device=f"cuda:{local}", seed=1234, env_offset=rank * n, **WORKLOAD)
-            net = ForwardGaussianPolicy(envr.obs_dim, envr.action_dim, device=f"cuda:{local}")
-            ro = Rollout(envr, net, 32, seed=1234, training=True, use_graph=True)
-            perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-            for g in range(8):                  # de-synchronise the episodes: 8 groups, 32 control steps apart (untimed)
-                idx = perm[g * n // 8:(g + 1) * n // 8]
-                ro._cur[idx] = envr.reset(idx.to(torch.int32))
-                ro.collect()
-            T.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(20):
-                ro.collect()
-            b.record(); T.barrier()
-            tr = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-            extras["rollout_with_policy"] = {
-                "what": "ForwardGaussianPolicy(200-100) perform + env step + filter update per control step, CUDA graph of 32 steps",
-                "ms_per_control_step": float(tr.item()) / 640, "value": world * n * 640 / (float(tr.item()) * 1e-3), "unit": "env-steps/s",
-                "kernels_per_control_step": 3}
-            envr.close(); net.close()
-        except Exception as e:
-            extras["rollout_with_policy"] = {"error": repr(e)}
+        def rollout_extra(name, nr, tensor_cores):
+            try:
+                from rex_gym_b200.agents import ForwardGaussianPolicy, Rollout
+                envr = R.BatchedRexEnv(num_envs=nr, device=f"cuda:{local}", seed=1234, env_offset=rank * nr, **WORKLOAD)
+                net = ForwardGaussianPolicy(envr.obs_dim, envr.action_dim, device=f"cuda:{local}", tensor_cores=tensor_cores)
+                ro = Rollout(envr, net, 32, seed=1234, training=True, use_graph=True)
+                perm = torch.randperm(nr, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+                for g in range(8):                  # de-synchronise the episodes: 8 groups, 32 control steps apart (untimed)
+                    idx = perm[g * nr // 8:(g + 1) * nr // 8]
+                    ro._cur[idx] = envr.reset(idx.to(torch.int32))
+                    ro.collect()
+                T.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    ro.collect()
+                b.record(); T.barrier()
+                tr = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+                extras[name] = {
+                    "what": "ForwardGaussianPolicy(200-100) perform + env step + filter update per control step, CUDA graph of 32 steps"
+                            + ("; policy / value layer 2 on the tensor cores (tcgen05 kind::tf32)" if tensor_cores else "; networks in fp32 on the CUDA cores"),
+                    "envs_per_gpu": nr, "ms_per_control_step": float(tr.item()) / 640,
+                    "value": world * nr * 640 / (float(tr.item()) * 1e-3), "unit": "env-steps/s", "kernels_per_control_step": 3}
+                envr.close(); net.close()
+            except Exception as e:
+                extras[name] = {"error": repr(e)}
+        rollout_extra("rollout_with_policy", n, False)
+        rollout_extra("rollout_with_policy_65536", 65536, False)
+        rollout_extra("rollout_with_policy_65536_tf32_tensor_cores", 65536, True)
 
     if rank == 0:
         peaks = {}

@@ -46,6 +46,10 @@ int64_t rexagent_policy_floats(const RexAgentConfig* cfg);   /* padded size of t
 int64_t rexagent_value_floats(const RexAgentConfig* cfg);    /* padded size of the value block  */
 int rexagent_create(const RexAgentConfig* cfg, RexAgent** out);
 void rexagent_destroy(RexAgent* a);
+/* 0 (default): the networks in fp32 on the CUDA cores -- matches an fp32 reference to rounding.
+ * 1: layer 2 (hidden1 x hidden2, 97 % of the flops) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with fp32
+ *    accumulation in TMEM (operands rounded to 11 significant bits; measured error in DESIGN.md).  Needs hidden1 % 8 == 0, obs_dim <= 16. */
+int rexagent_set_precision(RexAgent* a, int32_t mode);
 int rexagent_set_params(RexAgent* a, const float* host_params, int64_t n_floats);
 int rexagent_get_params(RexAgent* a, float* host_params, int64_t n_floats);
 /* device pointer to the packed block (a learner updates it in place) */

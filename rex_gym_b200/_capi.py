@@ -33,7 +33,7 @@ class RexAgentConfig(C.Structure):
                 ("observ_clip", C.c_float), ("reward_clip", C.c_float)]
 
 
-AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_create", "rexagent_destroy", "rexagent_set_params",
+AGENT_EXPORTS = ["rexagent_policy_floats", "rexagent_value_floats", "rexagent_create", "rexagent_destroy", "rexagent_set_precision", "rexagent_set_params",
                  "rexagent_get_params", "rexagent_params_buffer", "rexagent_state_buffers", "rexagent_set_filters", "rexagent_get_filters",
                  "rexagent_perform", "rexagent_experience", "rexagent_experience_partial", "rexagent_experience_finalize", "rexagent_transform_reward", "rexagent_discounted_return",
                  "rexagent_lambda_advantage", "rexagent_gae_segments", "rexagent_launch_count"]
@@ -91,6 +91,7 @@ def load():
     L.rexagent_value_floats.argtypes = [cfgp]; L.rexagent_value_floats.restype = C.c_int64
     L.rexagent_create.argtypes = [cfgp, C.POINTER(C.c_void_p)]
     L.rexagent_destroy.argtypes = [C.c_void_p]; L.rexagent_destroy.restype = None
+    L.rexagent_set_precision.argtypes = [C.c_void_p, C.c_int32]
     L.rexagent_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.rexagent_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.rexagent_params_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]

@@ -28,7 +28,7 @@ class ForwardGaussianPolicy(object):
     """policy_layers / value_layers must both be (H1, H2) (every config the reference ships uses (200, 100))."""
 
     def __init__(self, observ_size, action_size, policy_layers=(200, 100), value_layers=(200, 100), init_logstd=-1.0,
-                 init_mean_factor=0.1, device="cuda:0", seed=0):
+                 init_mean_factor=0.1, device="cuda:0", seed=0, tensor_cores=False):
         if tuple(policy_layers) != tuple(value_layers) or len(policy_layers) != 2:
             raise ValueError("policy_layers and value_layers must be the same two sizes")
         if not torch.cuda.is_available():
@@ -44,6 +44,12 @@ class ForwardGaussianPolicy(object):
         with torch.cuda.device(self.device):
             _capi.check(self._L.rexagent_create(C.byref(c), C.byref(h)))
         self._h = h
+        # tensor_cores=True: layer 2 (97 % of the flops) as tcgen05.mma kind::tf32 with fp32 accumulation in TMEM; operands keep 11
+        # significant bits (error vs the fp32 kernel: DESIGN.md section 5).  False (default): fp32 on the CUDA cores.
+        self.tensor_cores = bool(tensor_cores)
+        if self.tensor_cores:
+            with torch.cuda.device(self.device):
+                _capi.check(self._L.rexagent_set_precision(self._h, 1))
         pf, pc = C.c_void_p(), C.c_void_p()
         _capi.check(self._L.rexagent_state_buffers(self._h, C.byref(pf), C.byref(pc)))
         from ..envs.batched_env import _DevArray

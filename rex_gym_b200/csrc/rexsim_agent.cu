@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <type_traits>
 
 namespace rexsim {
 void set_error(const char* msg);   // rexsim_capi.cu (message returned by rexsim_last_error)
@@ -209,6 +210,271 @@ __global__ void __launch_bounds__(512, 1) perform_kernel(const PerformArgs P) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// perform on the 5th-generation tensor cores (opt-in: rexagent_set_precision(a, 1)).
+//
+// Layer 2 (H1 x H2 = 200 x 100, 97 % of the network's flops) runs as ONE tcgen05.mma chain per 128-env tile:
+//   D[128 envs][N] (fp32, TMEM) = A[128][H1] (layer-1 activations, shared memory) x B[N][H1]^T (W2^T, shared memory),
+// kind::tf32 (operands rounded to 10-bit mantissas with cvt.rna, fp32 accumulation), M = 128, N = H2 rounded up to 16,
+// K = 8 per instruction, H1 / 8 instructions issued by one thread; completion arrives on an mbarrier (tcgen05.commit);
+// the eight warps read the accumulators back (tcgen05.ld 32x32b: a warp reaches the TMEM lanes of its quarter, 32 envs; two
+// warps per quarter split the columns) and finish bias, ReLU, head and sampling one env per thread.  Layer 1 (O <= 16 inputs) and the head stay on the CUDA cores in fp32.
+//
+// Operand layout in shared memory: K-major, no swizzle (UMMA "interleave"): 8-row x 16-byte core matrices (8 rows x 4
+// tf32), the two core matrices one instruction reads along K are LBO bytes apart, 8-row groups SBO = 128 bytes apart:
+//   byte(row, k) = (k / 4) * LBO + (row / 8) * 128 + (row % 8) * 16 + (k % 4) * 4,   LBO = rows * 16.
+// Layer 1 writes A directly in that form (one 16-byte store per (env, 4 hidden units)).
+// TF32 keeps 11 significant bits: the measured error against the fp32 kernel is stated in DESIGN.md; the fp32 FFMA2
+// kernel above stays the parity default.
+// -------------------------------------------------------------------------------------------------------------------
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets (16-byte units),
+// version 1 (Blackwell), no swizzle, base offset 0
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+// both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_a, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+    }
+}
+constexpr int TM = 128, THREADS = 256, TMEM_COLS = 128;
+}  // namespace tc
+
+static size_t perform_tc_smem_bytes(const RexAgentConfig* c) {
+    const int npad = (c->hidden2 + 15) & ~15;
+    const size_t a = (size_t)tc::TM * c->hidden1 * 4, b = (size_t)npad * c->hidden1 * 4;
+    const size_t small = ((size_t)c->obs_dim * c->hidden1 + c->hidden1 + c->hidden2 + (size_t)c->hidden2 * AG_MAX_A + 2 * AG_MAX_A +
+                          (size_t)c->obs_dim * tc::TM + 2 * AG_MAX_O) * 4;
+    return a + b + small + 64;
+}
+
+// OT / AT: obs_dim / action_dim known at compile time (0 = generic: loops over the maxima with predicates -- every predicated-off
+// instruction still takes an issue slot, which made the generic form 4x heavier than needed for the reference's 4-in / 2-out nets)
+template <int OT, int AT>
+__global__ void __launch_bounds__(tc::THREADS, 1) perform_tc_kernel(const PerformArgs P) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smraw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const RexAgentConfig& c = P.D.cfg;
+    const int O = OT ? OT : c.obs_dim, A = AT ? AT : c.action_dim, H1 = c.hidden1, H2 = c.hidden2;
+    constexpr int OU = OT ? OT : 16;                        // unroll bound of the input loops
+    const int NP = (H2 + 15) & ~15;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int net = blockIdx.y;
+    const int AO = net == 0 ? A : 1;
+    const uint32_t LBO_A = TM * 16, LBO_B = (uint32_t)NP * 16;
+    uint8_t* Asm = smraw;                                   // [H1/4][TM/8][8][16 B]
+    uint8_t* Bsm = Asm + (size_t)TM * H1 * 4;               // [H1/4][NP/8][8][16 B]
+    float* W1 = reinterpret_cast<float*>(Bsm + (size_t)NP * H1 * 4);   // [O][H1]
+    float* b1 = W1 + O * H1;
+    float* b2 = b1 + H1;
+    float* W3 = b2 + H2;                                    // [H2][AO]
+    float* b3 = W3 + H2 * AG_MAX_A;                         // b3[AO], then logstd[AO]
+    float* xs = b3 + 2 * AG_MAX_A;                          // [O][TM]
+    float* nrm = xs + O * TM;                               // [2][O]
+    const float* G = P.D.params + (net == 0 ? 0 : P.D.pol_floats);
+    const float* gW1 = G; const float* gb1 = gW1 + O * H1; const float* gW2 = gb1 + H1; const float* gb2 = gW2 + H1 * H2;
+    const float* gW3 = gb2 + H2; const float* gb3 = gW3 + H2 * AO;
+    const uint32_t bar_a = smem_u32(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {                                        // one warp allocates the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < O) {   // StreamingNormalize.transform constants (normalize.py:57-66, _std :131-144)
+        const int cnt = P.D.cnt[0];
+        float m = P.D.filt[tid], vs = P.D.filt[O + tid];
+        float inv = 1.f;
+        if (cnt > 1) inv = 1.f / (sqrtf(vs / (float)(cnt - 1) + 1e-4f) + 1e-8f);
+        nrm[tid] = m; nrm[O + tid] = inv;
+    }
+    // weights: the small layers as they are, W2 transposed into the B operand form (rounded to tf32, zero rows up to NP)
+    for (int i = tid; i < O * H1; i += THREADS) W1[i] = gW1[i];
+    for (int i = tid; i < H1; i += THREADS) b1[i] = gb1[i];
+    for (int i = tid; i < H2; i += THREADS) b2[i] = gb2[i];
+    for (int i = tid; i < H2 * AO; i += THREADS) W3[i] = gW3[i];
+    if (tid < 2 * AO) b3[tid] = gb3[tid];                   // b3[AO] followed by logstd[AO] (policy block; unused for the value net)
+    {   // W2 [H1][H2] row-major -> B[n][k]: 16-byte global loads (4 consecutive n of one k), several in flight per thread
+        const int nq = NP >> 2;
+#pragma unroll 4
+        for (int i = tid; i < nq * H1; i += THREADS) {
+            const int k = i / nq, n = (i - k * nq) << 2;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < H2) w = *reinterpret_cast<const float4*>(gW2 + (size_t)k * H2 + n);        // H2 is a multiple of 4
+            uint8_t* dst = Bsm + (size_t)(k >> 2) * LBO_B + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4;
+            *reinterpret_cast<float*>(dst) = to_tf32(w.x); *reinterpret_cast<float*>(dst + 16) = to_tf32(w.y);
+            *reinterpret_cast<float*>(dst + 32) = to_tf32(w.z); *reinterpret_cast<float*>(dst + 48) = to_tf32(w.w);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // B was written through the generic proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = instr_desc_tf32(TM, NP);
+    const uint32_t a_addr = smem_u32(Asm), b_addr = smem_u32(Bsm);
+    const int ntiles = (P.n + TM - 1) / TM;
+    const uint32_t step = P.step + (uint32_t)P.D.cnt[2];
+    uint32_t phase = 0;
+    // normalised observations of a tile -> xs (coalesced read of the [TM][O] block).  Issued for the first tile here and for
+    // tile t + 1 right after layer 1 of tile t, so the global loads are in flight while the MMA chain and the epilogue run.
+    auto load_obs = [&](int tile) {
+        const int e0 = tile * TM;
+        for (int i = tid; i < TM * O; i += THREADS) {
+            const int e = i / O, o = i - e * O;
+            float v = 0.f;
+            if (e0 + e < P.n) {
+                v = P.observ[(size_t)(e0 + e) * O + o];
+                if (net == 0 && P.observ_copy) P.observ_copy[(size_t)(e0 + e) * O + o] = v;
+            }
+            v = (v - nrm[o]) * nrm[O + o];
+            v = fminf(fmaxf(v, -c.observ_clip), c.observ_clip);
+            xs[o * TM + e] = v;
+        }
+    };
+    if ((int)blockIdx.x < ntiles) load_obs(blockIdx.x);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, phase ^= 1u) {
+        const int e0 = tile * TM;
+        __syncthreads();
+        // layer 1 -> A operand: thread = (env, half of the hidden units); the env's inputs stay in registers, the weight rows
+        // are warp-wide broadcast loads, every 4 hidden units leave as one 16-byte store into the core-matrix layout
+        {
+            const int e = tid & (TM - 1), half = tid >> 7;              // THREADS == 2 * TM
+            float x[OU];
+#pragma unroll
+            for (int o = 0; o < OU; o++) x[o] = (OT || o < O) ? xs[o * TM + e] : 0.f;
+            const int nk4 = H1 >> 2, k_lo = half ? (nk4 + 1) / 2 : 0, k_hi = half ? nk4 : (nk4 + 1) / 2;
+            uint8_t* dst = Asm + (e >> 3) * 128 + (e & 7) * 16;
+#pragma unroll 2
+            for (int k4 = k_lo; k4 < k_hi; k4++) {
+                float4 s4 = *reinterpret_cast<const float4*>(b1 + 4 * k4);
+#pragma unroll
+                for (int o = 0; o < OU; o++) {
+                    if (OT || o < O) {
+                        const float4 w = *reinterpret_cast<const float4*>(W1 + o * H1 + 4 * k4);
+                        s4.x = fmaf(x[o], w.x, s4.x); s4.y = fmaf(x[o], w.y, s4.y); s4.z = fmaf(x[o], w.z, s4.z); s4.w = fmaf(x[o], w.w, s4.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(dst + (size_t)k4 * LBO_A) =
+                    make_float4(to_tf32(fmaxf(s4.x, 0.f)), to_tf32(fmaxf(s4.y, 0.f)), to_tf32(fmaxf(s4.z, 0.f)), to_tf32(fmaxf(s4.w, 0.f)));
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // A: generic-proxy writes -> tensor-core (async proxy) reads
+        __syncthreads();
+        if (tid == 0) {                                     // the MMA chain: H1 / 8 instructions, one issuing thread
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < (H1 >> 3); kb++) {
+                const uint64_t da = smem_desc(a_addr + (uint32_t)kb * 2u * LBO_A, LBO_A, 128u);
+                const uint64_t db = smem_desc(b_addr + (uint32_t)kb * 2u * LBO_B, LBO_B, 128u);
+                mma_tf32(tmem_base, da, db, idesc, kb > 0 ? 1u : 0u);
+            }
+            // completion of everything issued so far -> one arrival on the mbarrier (implies tcgen05.fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_a) : "memory");
+        }
+        if (tile + (int)gridDim.x < ntiles) load_obs(tile + gridDim.x);      // xs is free again: next tile's loads fly during the MMA chain
+        auto epilogue = [&](auto ao_tag) {
+            constexpr int AC = decltype(ao_tag)::value;          // head width at compile time (0: generic, predicated up to AG_MAX_A)
+            constexpr int AU = AC ? AC : AG_MAX_A;
+            // epilogue on all 8 warps: warp w may read TMEM lanes 32 (w % 4) .. +31, so warps w and w + 4 share a quarter of the
+            // envs and split the accumulator columns in two halves; thread <-> env e0 + 32 (w % 4) + lane.  The upper half hands
+            // its partial head sums over through shared memory (the A operand's first bytes: the MMA chain is done with it).
+            mbar_wait(bar_a, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3, hi = warp >> 2;
+            const int el = q * 32 + (tid & 31);
+            const int env = e0 + el;
+            float sh[AU];
+#pragma unroll
+            for (int a = 0; a < AU; a++) sh[a] = ((AC || a < AO) && !hi) ? b3[a] : 0.f;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int chunks = NP >> 4, c_lo = hi ? (chunks + 1) / 2 : 0, c_hi = hi ? chunks : (chunks + 1) / 2;
+            for (int cc = c_lo; cc < c_hi; cc++) {
+                const int c0 = cc << 4;
+                uint32_t r[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(lane_addr + (uint32_t)c0) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const int n = c0 + 4 * j4;
+                    if (n < H2) {                                       // H2 is a multiple of 4: whole groups only
+                        const float4 bb = *reinterpret_cast<const float4*>(b2 + n);
+                        const float h0 = fmaxf(__uint_as_float(r[4 * j4]) + bb.x, 0.f), h1v = fmaxf(__uint_as_float(r[4 * j4 + 1]) + bb.y, 0.f);
+                        const float h2v = fmaxf(__uint_as_float(r[4 * j4 + 2]) + bb.z, 0.f), h3v = fmaxf(__uint_as_float(r[4 * j4 + 3]) + bb.w, 0.f);
+                        const float* w3 = W3 + n * AO;
+#pragma unroll
+                        for (int a = 0; a < AU; a++)
+                            if (AC || a < AO) sh[a] = fmaf(h3v, w3[3 * AO + a], fmaf(h2v, w3[2 * AO + a], fmaf(h1v, w3[AO + a], fmaf(h0, w3[a], sh[a]))));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            float* part = reinterpret_cast<float*>(Asm);    // [AG_MAX_A][TM] partial sums of the upper column half
+            if (hi) {
+#pragma unroll
+                for (int a = 0; a < AU; a++) if (AC || a < AO) part[a * TM + el] = sh[a];
+            }
+            __syncthreads();
+            if (!hi) {
+#pragma unroll
+                for (int a = 0; a < AU; a++) if (AC || a < AO) sh[a] += part[a * TM + el];
+            }
+            if (!hi && env < P.n) {
+                if (net == 1) {
+                    if (P.value) P.value[env] = sh[0];
+                } else {
+                    float lp = 0.f;
+#pragma unroll
+                    for (int a = 0; a < AU; a++) {
+                        if (AC || a < A) {
+                            const float mu = tanhf(sh[a]);
+                            const float ls = b3[AO + a];
+                            float act = mu, z = 0.f;
+                            if (P.training) {               // network.policy.sample (algorithm.py:116)
+                                const uint32_t genv = P.env_offset + (uint32_t)env;
+                                const float u1 = ((float)(rand_u32(P.seed, genv, step, 2 * a) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                                const float u2 = ((float)(rand_u32(P.seed, genv, step, 2 * a + 1) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                                z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+                                act = fmaf(expf(ls), z, mu);
+                            }
+                            lp += -0.5f * z * z - ls - 0.9189385332046727f;     // diag-normal log-density
+                            if (P.action) P.action[(size_t)env * A + a] = act;
+                            if (P.mean) P.mean[(size_t)env * A + a] = mu;
+                        }
+                    }
+                    if (P.logprob) P.logprob[env] = lp;
+                }
+            }
+        };
+        if (net == 1) epilogue(std::integral_constant<int, 1>{});
+        else epilogue(std::integral_constant<int, AT>{});
+        __syncthreads();                                    // accumulators read, A free: next tile
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
 // StreamingNormalize.update for the observation columns and the reward column in one launch (normalize.py:73-99):
 // per column j: S1 = sum(x - mean), S2 = sum((x - mean)^2) over the batch (block partials, then the last block to
 // finish adds them in a fixed order -> bit-reproducible); count += n; new_mean = mean + S1/count;
@@ -376,7 +642,17 @@ struct RexAgent {
     float* d_partial = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
+    int precision = 0;                 // 0: fp32 on the CUDA cores (parity default); 1: layer 2 on the tensor cores in TF32
 };
+
+// the instance compiled for this network's input / output widths (the reference's tasks: 4 or 16 observations, 1-8 actions)
+typedef void (*PerformTcKernel)(const PerformArgs);
+static PerformTcKernel perform_tc_pick(const RexAgentConfig* c) {
+    const int O = c->obs_dim, A = c->action_dim;
+    if (O == 4) { if (A == 1) return perform_tc_kernel<4, 1>; if (A == 2) return perform_tc_kernel<4, 2>; if (A == 8) return perform_tc_kernel<4, 8>; return perform_tc_kernel<4, 0>; }
+    if (O == 16) { if (A == 2) return perform_tc_kernel<16, 2>; if (A == 4) return perform_tc_kernel<16, 4>; return perform_tc_kernel<16, 0>; }
+    return perform_tc_kernel<0, 0>;
+}
 
 static int afail(int code, const char* msg) { set_error(msg); return code; }
 #define ACK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { char b[256]; snprintf(b, sizeof(b), "%s: %s", #x, cudaGetErrorString(_e)); set_error(b); return REXSIM_ERR_CUDA; } } while (0)
@@ -444,6 +720,18 @@ void rexagent_destroy(RexAgent* a) {
     cudaFree(a->d_params); cudaFree(a->d_filt); cudaFree(a->d_cnt); cudaFree(a->d_partial);
     delete a;
 }
+int rexagent_set_precision(RexAgent* a, int32_t mode) {
+    if (!a) return afail(REXSIM_ERR_INVALID, "null argument");
+    if (mode != 0 && mode != 1) return afail(REXSIM_ERR_INVALID, "agent: precision must be 0 (fp32) or 1 (tf32 tensor cores)");
+    if (mode == 1) {
+        const RexAgentConfig* c = &a->D.cfg;
+        if ((c->hidden1 & 7) || c->obs_dim > 16 || perform_tc_smem_bytes(c) > 227 * 1024)
+            return afail(REXSIM_ERR_UNSUPPORTED, "agent: the tensor-core path needs hidden1 % 8 == 0, obs_dim <= 16 and operands that fit 227 KB of shared memory");
+        ACK(cudaFuncSetAttribute(perform_tc_pick(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perform_tc_smem_bytes(c)));
+    }
+    a->precision = mode;
+    return REXSIM_OK;
+}
 int rexagent_set_params(RexAgent* a, const float* h, int64_t n) {
     if (!a || !h) return afail(REXSIM_ERR_INVALID, "null argument");
     if (n != (int64_t)a->D.pol_floats + a->D.val_floats) return afail(REXSIM_ERR_INVALID, "agent: parameter block size mismatch");
@@ -499,6 +787,15 @@ int rexagent_perform(RexAgent* a, const float* observ, int32_t n, int32_t traini
     PerformArgs P;
     P.D = a->D; P.observ = observ; P.n = n; P.training = training; P.seed = seed; P.step = step; P.env_offset = env_offset;
     P.action = action; P.mean = mean; P.logprob = logprob; P.value = value; P.observ_copy = observ_copy;
+    if (a->precision == 1) {          // tcgen05 path: 128-env tiles, one CTA per SM, networks in different CTAs (blockIdx.y)
+        const int half_tc = a->sm_count / 2 > 0 ? a->sm_count / 2 : 1;
+        const int nt = (n + tc::TM - 1) / tc::TM;
+        dim3 grid_tc(nt < half_tc ? nt : half_tc, 2);
+        perform_tc_pick(&a->D.cfg)<<<grid_tc, tc::THREADS, perform_tc_smem_bytes(&a->D.cfg), (cudaStream_t)stream>>>(P);
+        ACK(cudaGetLastError());
+        a->launches++;
+        return REXSIM_OK;
+    }
     // one CTA per SM (the weights fill most of the shared memory); the two networks run in different CTAs (blockIdx.y).
     // Small batches use 64-env tiles so that more SMs get a tile, large ones 128-env tiles (8 x 4 register tile per thread).
     const int half = a->sm_count / 2 > 0 ? a->sm_count / 2 : 1;

@@ -17,7 +17,7 @@ def test_agent_abi_exports_every_declared_symbol():
     L = _capi.load()
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rexsim_agent.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(rexagent_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) == 19 and sorted(_capi.AGENT_EXPORTS) == names
+    assert len(names) == 20 and sorted(_capi.AGENT_EXPORTS) == names
     for n in names:
         assert hasattr(L, n), n
     cfg = _capi.RexAgentConfig(4, 2, 200, 100, 5.0, 10.0)

@@ -21,6 +21,40 @@ def _random_weights(rng, O, A, H1=200, H2=100):
     return w
 
 
+@pytest.mark.parametrize("O,A,n", [(4, 2, 4096), (16, 4, 1000), (4, 1, 77), (16, 2, 65536), (8, 3, 300), (4, 5, 129)])
+def test_perform_on_the_tensor_cores(O, A, n):
+    """tensor_cores=True: layer 2 as tcgen05.mma kind::tf32 (operands rounded to 11 significant bits, fp32 accumulation in
+    TMEM).  Against the fp64 oracle and against the fp32 kernel on the same inputs: mean (after tanh) and value within 5e-3
+    (measured worst case over 65 536 x 16-input samples with activations up to +-5: 2.8e-3; 7e-4 on the 4-input networks; a K = 200
+    dot product of O(1) terms at 2^-11 relative operand error), sampling noise identical (it does not pass through the GEMM)."""
+    from rex_gym_b200.agents import ForwardGaussianPolicy
+    rng = np.random.default_rng(O * 100 + A + 7)
+    w = _random_weights(rng, O, A)
+    f = AO.StreamingNormalize((O,), True, True, 5)
+    f.update(rng.normal(0.3, 1.7, (5000, O)))
+    obs = (rng.normal(0.3, 3.0, (n, O))).astype(np.float32)
+    x = torch.from_numpy(obs).cuda()
+    outs = {}
+    for tcore in (False, True):
+        net = ForwardGaussianPolicy(O, A, tensor_cores=tcore)
+        net.set_weights(w)
+        net.set_filters(f.count, f.mean, f.var_sum, 0, 0.0, 0.0)
+        outs[tcore] = {k: t.cpu().numpy() for k, t in net.perform(x, training=True, seed=3, step=2, env_offset=10).items()}
+        outs[tcore]["det"] = net.perform(x, training=False)["action"].cpu().numpy()
+        net.close()
+    sub = slice(0, min(n, 1024))
+    _, m, _, v = AO.perform(w, f, obs[sub], False)
+    g, r = outs[True], outs[False]
+    em, ev = np.abs(g["mean"][sub] - m).max(), np.abs(g["value"][sub] - v).max()
+    print("tf32 perform vs oracle: mean %.2e value %.2e; vs fp32 kernel: mean %.2e value %.2e" % (
+        em, ev, np.abs(g["mean"] - r["mean"]).max(), np.abs(g["value"] - r["value"]).max()))
+    assert em < 5e-3 and ev < 5e-3
+    assert np.abs(g["mean"] - r["mean"]).max() < 5e-3 and np.abs(g["value"] - r["value"]).max() < 5e-3
+    assert np.abs(g["mean"] - r["mean"]).mean() < 3e-4                                        # typical error: 1e-4
+    assert np.abs((g["action"] - g["mean"]) - (r["action"] - r["mean"])).max() < 1e-5      # same noise draw on both paths
+    assert np.abs(g["det"] - g["mean"]).max() == 0 and np.isfinite(g["logprob"]).all()
+
+
 @pytest.mark.parametrize("O,A,n", [(4, 2, 4096), (16, 4, 1000), (4, 1, 64), (4, 8, 77), (16, 2, 65536)])
 def test_perform_matches_the_oracle(O, A, n):
     from rex_gym_b200.agents import ForwardGaussianPolicy
