@@ -265,7 +265,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     import rex_gym_b200 as R
     from rex_gym_b200 import sharding
     n = args.envs_per_gpu
