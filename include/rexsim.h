@@ -153,6 +153,9 @@ int rexsim_get_state(RexSim* sim, float* out_f, int32_t* out_i, void* stream);
 int rexsim_set_state(RexSim* sim, const float* in_f, void* stream);
 /* raw SoA state for checkpoint/resume: [n_float][N] f32 and [n_int][N] i32 device buffers */
 int rexsim_state_buffers(RexSim* sim, float** state_f, int32_t** state_i);
+/* sensor history ring (sensor model on): dev [depth][words][N] f32, words = 43 (61 with the arm); n_floats = 0 and ring = NULL when
+ * the model is off.  Part of an exact checkpoint together with the state buffers. */
+int rexsim_history_buffer(RexSim* sim, float** ring, int64_t* n_floats);
 /* dev [N + 1] int32: word e = error bits of env e's most recent step (cleared by a reset of that env); word N = OR of every
  * bit raised since it was last cleared.  rexsim_step_host clears the aggregate after copying it out (per-step semantics, like
  * ConvertTo32Bit raising for the offending step only, wrappers.py:522-543); device-path callers use rexsim_clear_errors. */

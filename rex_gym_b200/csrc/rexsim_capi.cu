@@ -284,6 +284,12 @@ int rexsim_state_buffers(RexSim* s, float** state_f, int32_t** state_i) {
     if (state_i) *state_i = s->d_si;
     return REXSIM_OK;
 }
+int rexsim_history_buffer(RexSim* s, float** ring, int64_t* n_floats) {
+    if (!s || !ring || !n_floats) return fail(REXSIM_ERR_INVALID, "null argument");
+    *ring = s->d_ring;
+    *n_floats = s->d_ring ? (int64_t)s->P.ring_depth * (s->P.cfg.num_motors == 18 ? HW_WORDS_ARM : HW_WORDS) * s->P.N : 0;
+    return REXSIM_OK;
+}
 int rexsim_error_flags(RexSim* s, int32_t** err_flags) {
     if (!s || !err_flags) return fail(REXSIM_ERR_INVALID, "null argument");
     *err_flags = s->d_err;

@@ -1948,6 +1948,7 @@ static cudaError_t launch_step_tsta(const Params& P, cudaStream_t st) {
     // hide the serial ABA / PGS chains) in larger CTAs; below that the 255-register build, lowest single-wave latency.
     // Measured crossovers (walk-ik flat 4096 / 16 384 envs: 0.142 / 0.229 ms small, 0.172 / 0.211 ms large; gallop-ol 16 384:
     // 0.257 / 0.206; turn-ik heightfield 16 384: 0.952 / 1.035), DESIGN.md section 5.
+    // (arm batches stay on the 255-register build: at 128 registers the arm's working set spills 4 KB, 1.23 vs 0.84 ms at 16 384 envs)
     bool big = !ARM && (P.N * 4 + 127) / 128 > (TERRAIN == REXSIM_TERRAIN_PLANE ? 2 : 4) * P.sm_count;
     if (const char* f = getenv("REXSIM_FORCE_BUILD")) big = !ARM && f[0] == 'b';      // developer A/B: "big" / "small"
     if (big) return launch_step_variant<TASK, SIGNAL, TERRAIN, ARM ? 1 : REXSIM_OCC_BIG, ARM, false, ARM ? REXSIM_BLOCK : REXSIM_BLOCK_BIG>(P, st);

@@ -191,6 +191,9 @@ class BatchedRexEnv(object):
         _capi.check(self._L.rexsim_state_buffers(self._h, C.byref(pf), C.byref(pi)))
         self._state_f = torch.as_tensor(_DevArray(pf.value, (nf.value, N), "<f4", self), device=dev)
         self._state_i = torch.as_tensor(_DevArray(pi.value, (ni.value, N), "<i4", self), device=dev)
+        pr, nr = C.c_void_p(), C.c_int64()
+        _capi.check(self._L.rexsim_history_buffer(self._h, C.byref(pr), C.byref(nr)))          # sensor history ring (None: model off)
+        self._ring = torch.as_tensor(_DevArray(pr.value, (nr.value,), "<f4", self), device=dev) if nr.value else None
         # spaces: raw task spaces, or the wrapper-visible ones when the training wrappers are fused in
         b = ACTION_BOUND[(task, signal_type)]
         if normalize:
@@ -354,11 +357,16 @@ class BatchedRexEnv(object):
 
     def state_dict(self):
         """Exact checkpoint of the whole batch (the reference never checkpoints env state)."""
-        return {"state_f": self._state_f.clone(), "state_i": self._state_i.clone()}
+        sd = {"state_f": self._state_f.clone(), "state_i": self._state_i.clone()}
+        if self._ring is not None:
+            sd["sensor_history"] = self._ring.clone()
+        return sd
 
     def load_state_dict(self, sd):
         self._state_f.copy_(sd["state_f"])
         self._state_i.copy_(sd["state_i"])
+        if self._ring is not None:
+            self._ring.copy_(sd["sensor_history"])
 
     @property
     def launch_count(self):

@@ -679,6 +679,24 @@ def test_sensor_latency_and_noise(task, sig, n, kw):
     env.close()
 
 
+def test_checkpoint_resume_is_exact_with_the_sensor_model():
+    """state_dict() carries the SoA state and, with the sensor model on, the history ring: a batch restored into a fresh handle
+    continues bit for bit (the reference never checkpoints env state)."""
+    kw = dict(target_position=2.0, backwards=False, control_latency=0.012, observation_noise_stdev=NOISE, auto_reset=True, max_episode_steps=25, seed=3)
+    a, b = _env("walk", 64, **kw), _env("walk", 64, **kw)
+    a.reset(); b.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    acts = torch.rand((40, 64, 2), device="cuda", generator=g) * 0.8 - 0.4
+    for k in range(17):
+        a.step(acts[k])
+    b.load_state_dict(a.state_dict())
+    for k in range(17, 40):
+        oa, ra, da, _ = a.step(acts[k]); ob, rb, db, _ = b.step(acts[k])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), k
+    assert "sensor_history" in a.state_dict()
+    a.close(); b.close()
+
+
 def test_sensor_model_off_is_the_reference_default():
     """control_latency = pd_latency = 0 and zero noise (rex_gym_env.py:61,70-71 defaults): no history is allocated and the kernels
     read the true state -- the same launches as before the sensor model existed."""
