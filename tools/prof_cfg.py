@@ -20,13 +20,16 @@ KW = {"C2": dict(task="walk", signal_type="ik", target_position=2.0, backwards=F
       "C4": dict(task="turn", signal_type="ik", terrain_type="random", num_fields=64),
       "C5": dict(task="standup", signal_type="ol", mark="arm"),
       "standup": dict(task="standup", signal_type="ol")}[cfg]
+if len(sys.argv) > 4:
+    common["rebalance_every"] = int(sys.argv[4])
 env = R.BatchedRexEnv(num_envs=n, **common, **KW)
 env.reset()
 acts = torch.rand((64, n, env.action_dim), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1234)) * 2 - 1
 stagger_episodes(env, acts)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); a.record()
-for k in range(steps):
-    env.step(acts[k % 64])
+for r in range(5):
+    for k in range(steps):
+        env.step(acts[k % 64])
 b.record(); torch.cuda.synchronize()
-print(cfg, n, "ms/step %.4f" % (a.elapsed_time(b) / steps), "errors", env.check_errors())
+print(cfg, n, "rebalance_every", common.get("rebalance_every", "default"), "ms/step %.4f" % (a.elapsed_time(b) / (5 * steps)), "errors", env.check_errors())
