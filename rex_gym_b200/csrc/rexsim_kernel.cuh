@@ -8,14 +8,17 @@
 //
 // One launch = one RexGymEnv.step for every env (rex_gym/envs/rex_gym_env.py:369-414):
 //   task signal (Bezier gait + 3-DOF leg IK or open loop)      envs/gym/*_env.py, model/gait_planner.py, model/kinematics.py
-//   action_repeat x { motor model (model/motor.py:76-143, model/rex.py:568-641)
-//                     + stepSimulation: ABA forward dynamics in a world-aligned common frame,
-//                       toe/ground contact, Delassus matrix, PGS (normal + 2 pyramid friction rows), integrate }
+//   action_repeat x { motor model (model/motor.py:76-143, model/rex.py:568-641), optionally on the PD-delayed observation
+//                     + stepSimulation: ABA forward dynamics in a world-aligned common frame, contact candidates (toe hull,
+//                       collision boxes) against the plane or the staged heightfield tile, joint-limit rows, PGS, integrate
+//                     + ReceiveObservation: push the sensor-history row (sensor model only, model/rex.py:726-733) }
 //   reward / termination / observation (+ fused ClipAction/RangeNormalize/LimitDuration, auto-reset)
 //
-// The physics is algebraically the same algorithm as oracle/rexsim_oracle.c (Bullet btMultiBody pipeline)
-// but formulated differently on purpose: common-frame ABA instead of link frames, impulse-space PGS on the
-// 12x12 Delassus matrix instead of generalized-velocity space.  Identical iterates in exact arithmetic.
+// The physics is algebraically the same algorithm as oracle/rexsim_oracle.c (Bullet btMultiBody pipeline) but formulated
+// differently on purpose: common-frame ABA instead of link frames; impulse-space PGS on the Delassus matrix of the foot
+// contacts, leg joint limits and arm joint limits (the fast path) or a matrix-free base / limb split (body contacts) instead of
+// generalized-velocity space.  Identical iterates in exact arithmetic.  The warps of a CTA re-align at every sub-step: the
+// straight-line code of one sub-step (150 KB) outruns the instruction caches otherwise.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
