@@ -131,7 +131,7 @@ void rexsim_destroy(RexSim* sim);
 int rexsim_step(RexSim* sim, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
 /* Host-buffer form of rexsim_step -- BatchEnv.step with numpy arrays (batch_env.py:63-90): h_actions HOST [N][A] f32,
  * h_out HOST block of rexsim_host_out_bytes() bytes laid out as obs [N][O] f32 | reward [N] f32 | done [N] u8 | pad to 4 |
- * int32 OR of all error flags.  One call = H2D copy of the actions, the step kernel, one D2H copy of the results (+4 bytes of
+ * int32 OR of all error flags | 8 scratch bytes (the kernel's flag bytes on the zero-copy path).  One call = H2D copy of the actions, the step kernel, one D2H copy of the results (+4 bytes of
  * flags) on `stream`, then a wait for that stream.  Pinned (page-locked) host memory gives the full copy speed; with pinned buffers
  * and N <= 16384 the kernel addresses the host block directly (zero-copy) and the two bulk copies disappear. */
 int64_t rexsim_host_out_bytes(const RexSim* sim);

@@ -209,7 +209,7 @@ static size_t out_done_offset(const RexSim* s) { return ((size_t)s->P.N * s->O +
 static size_t out_err_offset(const RexSim* s) { return (out_done_offset(s) + (size_t)s->P.N + 3) & ~(size_t)3; }
 int64_t rexsim_host_out_bytes(const RexSim* s) {
     if (!s) return 0;
-    return (int64_t)(out_err_offset(s) + sizeof(int32_t));
+    return (int64_t)(out_err_offset(s) + sizeof(int32_t) + 8);      // + 8 flag bytes the kernel sets directly on the zero-copy path
 }
 // true when p is page-locked host memory the device can address directly (UVA: same pointer value on both sides)
 static bool device_can_address(const void* p) {
@@ -223,12 +223,18 @@ int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* strea
     const size_t N = s->P.N;
     Params P = s->P;
     // Small batches with pinned buffers: the kernel reads the actions from, and writes its results into, the host block
-    // directly (zero-copy over PCIe) -- two DMA launches and their latencies less than the staged form.  Large batches
-    // stage through device buffers so the kernel never waits on PCIe.
+    // directly (zero-copy over PCIe) -- no DMA launches at all: the error bits travel as flag bytes the kernel sets in the
+    // block, the device-side aggregate is cleared BEFORE the kernel.  Large batches stage through device buffers so the kernel
+    // never waits on PCIe.
     const bool zero_copy = N <= 16384 && device_can_address(h_actions) && device_can_address(h_out);   // queried per call (~1 us)
+    int32_t* h_err = reinterpret_cast<int32_t*>((char*)h_out + out_err_offset(s));
+    uint8_t* h_flags = reinterpret_cast<uint8_t*>(h_err + 1);
     if (zero_copy) {
+        memset(h_flags, 0, 8);
+        CK(cudaMemsetAsync(s->d_err + N, 0, sizeof(int32_t), st));    // the aggregate is per step on the host path
         P.actions = h_actions;
         P.obs = (float*)h_out; P.reward = (float*)h_out + N * s->O; P.done = (uint8_t*)h_out + out_done_offset(s);
+        P.err_host = h_flags;
     } else {
         CK(cudaMemcpyAsync(s->d_act, h_actions, N * s->A * sizeof(float), cudaMemcpyHostToDevice, st));
         P.actions = s->d_act;
@@ -237,10 +243,17 @@ int rexsim_step_host(RexSim* s, const float* h_actions, void* h_out, void* strea
     cudaError_t e = launch_step(P, st);
     if (e != cudaSuccess) return cuda_fail(e, "step launch");
     s->launches++;
-    if (!zero_copy) CK(cudaMemcpyAsync(h_out, s->d_out, out_err_offset(s), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync((char*)h_out + out_err_offset(s), s->d_err + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemsetAsync(s->d_err + N, 0, sizeof(int32_t), st));        // the aggregate is per step on the host path
+    if (!zero_copy) {
+        CK(cudaMemcpyAsync(h_out, s->d_out, out_err_offset(s), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_err, s->d_err + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(s->d_err + N, 0, sizeof(int32_t), st));
+    }
     CK(cudaStreamSynchronize(st));
+    if (zero_copy) {
+        int32_t bits = 0;
+        for (int b = 0; b < 8; b++) if (h_flags[b]) bits |= 1 << b;
+        *h_err = bits;
+    }
     return REXSIM_OK;
 }
 

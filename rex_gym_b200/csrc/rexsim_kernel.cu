@@ -1814,7 +1814,13 @@ __global__ void __launch_bounds__(BLOCK, (OCC * 128) / BLOCK) step_kernel(const 
         // per-env word = the error bits of this env's most recent step (ConvertTo32Bit raises for the offending step only,
         // wrappers.py:522-523,542-543); the aggregate word [N] accumulates until the host reads and clears it
         P.err[env] = err;
-        if (err) atomicOr(&P.err[N], err);
+        if (err) {
+            atomicOr(&P.err[N], err);
+            if (P.err_host) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) if ((err >> b) & 1) P.err_host[b] = 1;
+            }
+        }
     }
     // ---- auto reset: done envs restart from the settled snapshot; obs = first observation of the new episode --
     if (c.auto_reset && done) {

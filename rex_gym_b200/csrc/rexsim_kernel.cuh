@@ -58,7 +58,9 @@ struct Params {
     const float* __restrict__ snap_f;  // [nsnap][NF] settled reset snapshots
     const int32_t* __restrict__ snap_i;// [nsnap][NI]
     const float* __restrict__ field_zoff; // [nfields]
-    int32_t* __restrict__ err;         // [N]
+    int32_t* __restrict__ err;         // [N] per-env bits of the most recent step, [N] = OR of all since last cleared
+    uint8_t* err_host;                 // host-buffer step with zero-copy buffers: 8 flag bytes in the caller's block, byte b = 1 when an
+                                       // env raised error bit b this step (idempotent stores, no atomics across PCIe); else null
     float* __restrict__ cmd_out;       // [num_motors][N]
     const float* __restrict__ actions; // [N][A]
     float* __restrict__ obs;           // [N][O]

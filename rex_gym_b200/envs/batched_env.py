@@ -178,7 +178,7 @@ class BatchedRexEnv(object):
         self._h_obs = ho[:nb_obs].view(np.float32).reshape(N, O)
         self._h_reward = ho[nb_obs:nb_obs + nb_rew].view(np.float32)
         self._h_done = ho[nb_obs + nb_rew:nb_obs + nb_rew + N].view(np.bool_)
-        self._h_err = ho[nb_out - 4:].view(np.int32)
+        self._h_err = ho[nb_out - 12:nb_out - 8].view(np.int32)      # int32 OR of the step's error bits (8 scratch bytes follow)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         p = C.c_void_p()
         _capi.check(self._L.rexsim_error_flags(self._h, C.byref(p)))
