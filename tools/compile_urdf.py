@@ -125,8 +125,9 @@ def shape_local_aabb_halfext(sh):
 def link_inertia_diag(link):
     """Bullet shape-derived inertia diagonal (see module docstring)."""
     m, shapes = link["mass"], link["shapes"]
-    if not shapes:
-        return np.zeros(3)
+    if not shapes:      # an empty btCompoundShape: its AABB is the margin alone (2 mm cube) -- 3.3e-7 kg m^2 for the 0.5 kg leg covers
+        l = 2 * URDF_MARGIN
+        return m / 12.0 * np.array([2 * l * l, 2 * l * l, 2 * l * l])
     ident = len(shapes) == 1 and not shapes[0]["xyz"].any() and not shapes[0]["rpy"].any()
     if ident and shapes[0]["kind"] == "box":
         lx, ly, lz = shapes[0]["size"]
