@@ -297,6 +297,18 @@ class OracleSim:
         self.L.rexo_transform_action(C.c_void_p(self.h), i, a.ctypes.data_as(C.c_void_p), cmd.ctypes.data_as(C.c_void_p))
         return cmd[:self.nm]
 
+    def wrap_action(self, action):
+        a = np.zeros(8); a[:self.A] = action
+        out = np.zeros(8)
+        self.L.rexo_wrap_action(C.c_void_p(self.h), a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out[:self.A]
+
+    def wrap_observation(self, raw):
+        r = np.zeros(4 + MAXDOF); r[:self.O] = raw
+        out = np.zeros(4 + MAXDOF, np.float32)
+        self.L.rexo_wrap_observation(C.c_void_p(self.h), r.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out[:self.O]
+
     def reward_done_obs(self, i=0):
         r, d = C.c_double(), C.c_int()
         obs = np.zeros(4 + MAXDOF)

@@ -1039,14 +1039,31 @@ static void action_bounds(const RexoSim* s, int j, double* lo, double* hi) {
         default: *lo = -0.1; *hi = 0.1; break;                                                         /* standup_env.py:99-101 */
     }
 }
+/* RangeNormalize._normalize_observ (wrappers.py:238-242) then ConvertTo32Bit._convert_observ (:522-527) */
+void rexo_wrap_observation(const RexoSim* s, const double* raw, float* out) {
+    for (int j = 0; j < s->obs_dim; j++) {
+        double v = raw[j];
+        if (s->c.normalize) { double lo, hi; obs_bounds(s, j, &lo, &hi); v = 2 * (v - lo) / (hi - lo) - 1; }
+        out[j] = (float)v;
+    }
+}
+/* ClipAction.step (wrappers.py:262-265: clip to the [-1, 1] box RangeNormalize shows) then RangeNormalize._denormalize_action
+ * (:232-236) onto the task env's own Box -- gallop's has low > high (gallop_env.py:128-130), so the map turns into -b * a */
+void rexo_wrap_action(const RexoSim* s, const double* act, double* out) {
+    for (int j = 0; j < s->act_dim; j++) {
+        double v = act[j];
+        if (s->c.normalize) {
+            double lo, hi; action_bounds(s, j, &lo, &hi);
+            v = clipd(v, -1.0, 1.0);
+            v = (v + 1) / 2 * (hi - lo) + lo;
+        }
+        out[j] = v;
+    }
+}
 static void write_obs(RexoSim* s, RexoEnv* e, float* out) {
     double o[4 + REXO_MAXDOF];
     env_observation(s, e, o);
-    for (int j = 0; j < s->obs_dim; j++) {
-        double v = o[j];
-        if (s->c.normalize) { double lo, hi; obs_bounds(s, j, &lo, &hi); v = 2 * (v - lo) / (hi - lo) - 1; }  /* wrappers.py:238-242 */
-        out[j] = (float)v;                                                                                  /* ConvertTo32Bit */
-    }
+    rexo_wrap_observation(s, o, out);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1198,15 +1215,7 @@ void rexo_reset(RexoSim* s, const int32_t* idx, int k, float* obs_out) {
 static void transform_action(RexoSim* s, RexoEnv* e, const double* act, double* cmd) {
     const RexoConfig* c = &s->c;
     double a[8] = {0};
-    for (int j = 0; j < s->act_dim; j++) {
-        double v = act[j];
-        if (c->normalize) {   /* ClipAction to [-1,1] then RangeNormalize._denormalize_action wrappers.py:218-236,262-265 */
-            double lo, hi; action_bounds(s, j, &lo, &hi);
-            v = clipd(v, -1.0, 1.0);
-            v = (v + 1) / 2 * (hi - lo) + lo;
-        }
-        a[j] = v;
-    }
+    rexo_wrap_action(s, act, a);
     switch (c->task) {
         case REXO_TASK_WALK: walk_command(s, e, a, cmd); break;
         case REXO_TASK_GALLOP: gallop_command(s, e, a, cmd); break;
