@@ -297,6 +297,12 @@ class OracleSim:
         self.L.rexo_transform_action(C.c_void_p(self.h), i, a.ctypes.data_as(C.c_void_p), cmd.ctypes.data_as(C.c_void_p))
         return cmd[:self.nm]
 
+    def apply_action(self, i, cmd):
+        c = np.zeros(MAXDOF); c[:self.nm] = cmd
+        tau = np.zeros(MAXDOF)
+        self.L.rexo_apply_action(C.c_void_p(self.h), i, c.ctypes.data_as(C.c_void_p), tau.ctypes.data_as(C.c_void_p))
+        return tau[:self.nm]
+
     def wrap_action(self, action):
         a = np.zeros(8); a[:self.A] = action
         out = np.zeros(8)

@@ -752,7 +752,7 @@ static void sensed_quat(RexoSim* s, RexoEnv* e, uint32_t site, real* q4) {
 /* ------------------------------------------------------------------------------------------- */
 /* Rex.ApplyAction + stepSimulation + ReceiveObservation: rex_gym/model/rex.py:158-163,568-641   */
 /* ------------------------------------------------------------------------------------------- */
-static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {
+static void apply_action(RexoSim* s, RexoEnv* e, const double* cmd, real* tau) {       /* Rex.ApplyAction rex.py:568-641 */
     const RexoModel* m = &s->m;
     int n = m->nmotor;
     double q[REXO_MAXDOF], qd[REXO_MAXDOF], kp[REXO_MAXDOF], kd[REXO_MAXDOF], ta[REXO_MAXDOF], to[REXO_MAXDOF];
@@ -764,7 +764,7 @@ static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {
         for (int i = 0; i < n; i++) { q[i] = pdo[i]; qd[i] = pdo[n + i]; }
     }
     rexo_motor_torque(n, cmd, q, qd, qd_true, kp, kd, ta, to);   /* rex.py:596-600 */
-    real tau[REXO_MAXDOF]; for (int j = 0; j < m->ndof; j++) tau[j] = 0;
+    for (int j = 0; j < m->ndof; j++) tau[j] = 0;
     for (int i = 0; i < n; i++) {                                /* overheat protection rex.py:601-608 */
         if (fabs(ta[i]) > 2.45) e->overheat[i] += 1; else e->overheat[i] = 0;
         if (e->overheat[i] > 1.0 / s->c.sim_dt) e->enabled[i] = 0;
@@ -772,8 +772,18 @@ static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {
         tau[m->motor_dof[i]] = e->enabled[i] ? ta[i] : 0.0;      /* rex.py:617-623 */
         e->cmd[i] = cmd[i];
     }
+}
+static void apply_action_and_step(RexoSim* s, RexoEnv* e, const double* cmd) {            /* one pass of Rex.Step's loop rex.py:158-163 */
+    real tau[REXO_MAXDOF];
+    apply_action(s, e, cmd, tau);
     step_simulation(s, e, tau);
     receive_observation(s, e);                                   /* rex.py:162 */
+}
+/* ApplyAction alone (no physics): the torque each motor joint would be driven with, for tests/golden/apply_action_golden.json.gz */
+void rexo_apply_action(RexoSim* s, int i, const double* cmd, double* tau_motor) {
+    real tau[REXO_MAXDOF];
+    apply_action(s, &s->env[i], cmd, tau);
+    for (int k = 0; k < s->m.nmotor; k++) tau_motor[k] = tau[s->m.motor_dof[k]];
 }
 void rexo_substep(RexoSim* s, int i, const double* cmd) { apply_action_and_step(s, &s->env[i], cmd); }
 void rexo_physics_only(RexoSim* s, int i, const double* tau) {
