@@ -141,6 +141,26 @@ def test_reference_surface_names():
     assert walk_env.RexWalkEnv and gallop_env.RexReactiveEnv and turn_env.RexTurnEnv and standup_env.RexStandupEnv
 
 
+def test_terrain_bank_is_what_the_reference_hands_to_pybullet():
+    """tests/golden/terrain_golden.json (tools/gen_terrain_golden.py): the heights the reference's unmodified Terrain class passed
+    to createCollisionShape for its first three terrains (construction, then two update_terrain() = two resets), as float32
+    hashes + samples.  Bank field k is bit-for-bit the k-th of them, in the product's bank and in the oracle's."""
+    import hashlib
+    import json
+    from rex_gym_b200 import terrain as T
+    from oracle.oracle import make_fields
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "terrain_golden.json")))
+    assert (g["rows"], g["columns"]) == (T.ROWS, T.COLUMNS) and g["mesh_scale"] == [T.CELL, T.CELL, 1] == g["update_mesh_scale"]
+    assert g["init_position_random"] == [0, 0, 0.21]
+    ours, orac = T.make_random_fields(3), make_fields(3)
+    for k, want in enumerate(g["fields"]):
+        for f in (ours[k], orac[k]):
+            flat = np.ascontiguousarray(f, np.float32).reshape(-1)
+            assert hashlib.sha256(flat.tobytes()).hexdigest() == want["sha256_float32"], k
+            np.testing.assert_array_equal(flat[::257], np.array(want["every_257th"], np.float32))
+        assert 0 <= want["min"] and want["max"] <= T.PERTURBATION
+
+
 def test_terrain_bank_follows_the_reference_stream():
     """field 0 = first generate_terrain() of the reference: random.seed(10), 2x2 blocks of U(0, 0.05)
     (rex_gym/model/terrain.py:26,36-44)."""
