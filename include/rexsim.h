@@ -100,7 +100,7 @@ typedef struct {
     int32_t env_offset;               /* global id of env 0 of this shard (multi-GPU): reset draws key on the global id */
     double gait_clock_scale;          /* GaitPlanner clock = simulation time x this.  1 = the deterministic simulation clock (DESIGN.md
                                        * section 2).  The reference reads the WALL clock (gait_planner.py:108-110); the walk-ik episodes stored
-                                       * in its shipped checkpoint ran at about 16 (tests/test_pybullet_goldens.py) */
+                                       * in its shipped checkpoint ran at about 9 (tests/test_pybullet_goldens.py) */
     float pose_values[5];             /* poses task: base_y, base_z, base_roll, base_pitch, base_yaw constructor arguments
                                        * (poses_env.py:49-53); all NaN = None: the pose rotates per reset, target drawn in range */
     /* sensor model (rex_gym/model/rex.py:122,726-769; constructor arguments rex_gym_env.py:61,70-71).  All zero = the reference

@@ -19,7 +19,7 @@ cfg.normalize, cfg.max_episode_steps, cfg.auto_reset, cfg.seed = 1, 2000, 0, 123
 cfg.friction, cfg.residual_threshold, cfg.erp_contact, cfg.erp_joint = 0.5, 1e-7, 0.08, 0.2
 tables, cfg.toe_npts = pack_model_tables("base"); cfg.toe_margin = -0.00025  # model_tables.TOE_MARGIN
 for k in range(5): cfg.pose_values[k] = float("nan")                        # poses task only
-cfg.gait_clock_scale = 1.0                                                 # GaitPlanner clock = simulation clock (16 ~ the wall clock of the reference's walk-ik training)
+cfg.gait_clock_scale = 1.0                                                 # GaitPlanner clock = simulation clock (9 ~ the wall clock of the reference's walk-ik training)
 cfg.contact_breaking, cfg.link_damping, cfg.max_coordinate_velocity = 0.00081, 0.04, 100.0   # model_tables
 cfg.control_latency = cfg.pd_latency = 0.0                                 # sensor model off (reference default); noise_stdev[5] = 0
 sim = C.c_void_p()

@@ -50,13 +50,15 @@ def main():
         print(name, os.path.basename(prefix), "memory", ob.shape, "->", out[name + "_observ"].shape)
     # walk-ik: NOT replayable step by step (the gait phase ran on the wall clock, gait_planner.py:108-110), kept for the
     # statistical test of the wall-clock emulation (gait_clock_scale): 300 steps of 6 episodes
-    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ik")), ["memory/Variable_1", "memory/Variable_2"])
+    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ik")), ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
     out["walk_ik_action"] = v["memory/Variable_2"][:6, :300].astype(np.float32)
     out["walk_ik_observ"] = v["memory/Variable_1"][:6, :301].astype(np.float32)
+    out["walk_ik_reward"] = v["memory/Variable_5"][:6, :300].astype(np.float32)      # carries the base x (forward term), see the tests
     # gallop-ik: same story (wall-clock gait), but the observation carries the 12 joint angles: 600 steps of 3 episodes
-    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "gallop", "ik")), ["memory/Variable_1", "memory/Variable_2"])
+    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "gallop", "ik")), ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
     out["gallop_ik_action"] = v["memory/Variable_2"][:3, :600].astype(np.float32)
     out["gallop_ik_observ"] = v["memory/Variable_1"][:3, :601].astype(np.float32)
+    out["gallop_ik_reward"] = v["memory/Variable_5"][:3, :600].astype(np.float32)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
