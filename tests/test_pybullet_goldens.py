@@ -108,10 +108,16 @@ def test_walk_open_loop_tracks_pybullet_over_25_episodes_x_600_steps():
     assert med(rp.mean(1)) < 2.5e-3 and med(rp.max(1)) < 8.0e-3 and rp.max() < 5.5e-2
 
 
-def _translation_replay(task, **kw):
+def _translation_replay(task, cfg=None, **kw):
     """Replay with our own base position kept: x_ours(t), and F(t) = recorded reward minus OUR non-forward terms ~ x_pybullet / target."""
+    import ctypes as C
     ac, R = G[task + "_ol_action"], G[task + "_ol_reward"]
     s = OracleSim(EPISODES, task, "ol", normalize=True, settle=2, target_position=3.0, **kw)
+    if cfg:
+        for k, v in cfg.items():
+            setattr(s.cfg, k, v)
+        s.L.rexo_destroy(s.h)
+        s.h = s.L.rexo_create(C.byref(s.model), C.byref(s.cfg))
     s.reset()
     X, Rours = np.zeros((EPISODES, STEPS)), np.zeros((EPISODES, STEPS))
     for t in range(STEPS):
@@ -277,6 +283,16 @@ def test_recorded_trajectories_identify_the_friction_coefficient():
         assert other > 2.5 * base, (mu, other, base)
     for mu in (0.45, 0.55):
         assert _mean_joint_error(steps=300, episodes=25, friction=mu) > 1.15 * _mean_joint_error(steps=300, episodes=25), mu
+    # the base translation read off the recorded rewards is sharper still: mean distance (control steps) between our and
+    # PyBullet's x = 0.05 m crossing over the 25 gallop episodes -- 0.52 at 0.5; 2.4 / 1.7 at 0.45 / 0.55; 7.3 / 6.4 at 0.35 / 1.0
+
+    def crossing_error(mu):
+        X, _, R = _translation_replay("gallop", cfg=dict(friction=mu))
+        t_rec = np.array([int(np.argmax(R[e] > 0.01)) for e in range(EPISODES)])
+        t_our = np.array([int(np.argmax(X[e] > 0.05)) for e in range(EPISODES)])
+        return float(np.abs(t_our - t_rec).mean())
+    e_half = crossing_error(0.5)
+    assert e_half < 0.9 and crossing_error(0.45) > 2.5 * e_half and crossing_error(0.55) > 2.0 * e_half
 
 
 def test_recorded_trajectories_select_the_link_damping_and_the_toe_reach():
