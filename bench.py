@@ -351,7 +351,7 @@ def main():
         extra("walk_ik_demo_clock_x4", dict(WORKLOAD, gait_clock_scale=DEMO_CLOCK), n)
         extra("north_star_size", WORKLOAD, 65536)
         extra("north_star_size_demo_clock_x4", dict(WORKLOAD, gait_clock_scale=DEMO_CLOCK), 65536)
-        extra("north_star_size_training_clock_x16", dict(WORKLOAD, gait_clock_scale=16.0), 65536)
+        extra("north_star_size_training_clock_x9", dict(WORKLOAD, gait_clock_scale=9.0), 65536)     # walk-ik training runs: DESIGN.md section 2
         # BASELINE.json configs[2..4]
         extra("C3_gallop_ol_rand_gains", dict(common, task="gallop", signal_type="ol", motor_kp_range=(0.8, 1.2), motor_kd_range=(0.01, 0.03)), 16384)
         c4 = 65536 // world if world >= 4 else 16384
