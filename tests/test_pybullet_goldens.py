@@ -310,10 +310,16 @@ def test_recorded_trajectories_select_the_link_damping_and_the_toe_reach():
     saved = O.TOE_MARGIN
     try:
         e_0 = _mean_joint_error(steps=20, episodes=25)
+
+        def crossing_error():                        # independent observable: the x = 0.05 m crossing read off the rewards
+            X, _, R = _translation_replay("gallop")
+            return float(np.abs(np.array([int(np.argmax(X[e] > 0.05)) - int(np.argmax(R[e] > 0.01)) for e in range(EPISODES)])).mean())
+        c_0 = crossing_error()                       # 0.52 control steps; 0.88 for the exact hull, 1.92 with the importer margin
         for m in (0.0, 0.001):                       # the exact hull / Bullet's 1 mm importer margin
             O.TOE_MARGIN = m
             e_m = _mean_joint_error(steps=20, episodes=25)
             assert e_m > 1.3 * e_0, (m, e_m, e_0)
+            assert crossing_error() > (1.3 if m == 0.0 else 2.5) * c_0, m
     finally:
         O.TOE_MARGIN = saved
 
