@@ -159,6 +159,44 @@ def test_base_translation_tracks_pybullet_through_the_recorded_rewards(task, kw)
     assert 0.97 < np.median(ratio) < 1.03 and ratio.min() > 0.85 and ratio.max() < 1.12, ratio
 
 
+def test_walk_open_loop_to_the_goal_brake_and_standstill_like_pybullet():
+    """Four recorded walk-ol episodes over 1200 control steps = 6 s: ramp up, walk 1.0-1.8 m to the goal, brake, stand still.
+    The goal is a per-episode random draw that was not stored; it is recovered from the recording itself -- the forward reward
+    jumps from 0 to x / target when x passes 0.05 m (rex_gym_env.py:516-520), so target = 0.05 m (+ at most one step's travel)
+    / jump.  With that target the open-loop replay reproduces what no observation channel carries: the step at which PyBullet's
+    base passed target + 0.15 m (the reward drops from 1 to target - x, :512-513) within 15 control steps after 450-620, and the
+    place where the robot finally stands, target + 0.29 ... 0.37 m recorded, within 2 cm; roll / pitch stay within a few mrad of
+    the recording through all three phases."""
+    ac, ob, rw = G["walk_ol_long_action"], denorm(G["walk_ol_long_observ"]), G["walk_ol_long_reward"]
+    for k in range(ac.shape[0]):
+        # the target from the jump: replay the first 200 steps once to know our own step travel at the crossing (~1 mm)
+        probe = OracleSim(1, "walk", "ol", normalize=True, settle=2, target_position=3.0, backwards=False)
+        probe.reset()
+        xs = []
+        for t in range(200):
+            probe.step(ac[k:k + 1, t]); xs.append(-probe.env(0).pos[0])
+        t_jump = int(np.argmax(rw[k] > 0.01))
+        assert rw[k, t_jump - 1] < 0.002 < 0.012 < rw[k, t_jump] and abs(int(np.argmax(np.array(xs) > 0.05)) - t_jump) <= 2
+        lo = 0.05 / (rw[k, t_jump] - rw[k, t_jump - 1])           # the other reward terms do not jump
+        target = lo * (1 + 0.5 * (xs[t_jump] - xs[t_jump - 1]) / 0.05)
+        assert 0.95 < target < 1.9
+        s = OracleSim(1, "walk", "ol", normalize=True, settle=2, target_position=float(target), backwards=False)
+        s.reset()
+        R, P = [], []
+        for t in range(1200):
+            o, r, d = s.step(ac[k:k + 1, t])
+            assert not d[0], (k, t)
+            R.append(float(r[0])); P.append(denorm(o)[0, :2])
+        R, P = np.array(R), np.array(P)
+        drop_rec, drop_our = int(np.argmax(np.diff(rw[k]) < -0.5)), int(np.argmax(np.diff(R) < -0.5))
+        assert 400 < drop_rec < 650 and abs(drop_our - drop_rec) <= 15, (k, drop_rec, drop_our)      # measured: ours 5, 8, 6, 6 steps early
+        assert rw[k, -1] < -0.25 and abs(R[-1] - rw[k, -1]) < 0.02, (k, R[-1], rw[k, -1])             # stands where PyBullet's stands (measured: within 1.3 cm after 1.4-2.1 m)
+        assert abs(R[-1] - R[-100]) < 2e-3 and abs(rw[k, -1] - rw[k, -100]) < 2e-3                   # ... and both stand still
+        err = np.abs(P - ob[k, 1:, :2]).max(1)
+        assert err[:400].mean() < 3e-3 and err[400:800].mean() < 8e-3 and err[800:].mean() < 9e-3, (k, err[:400].mean(), err[400:800].mean(), err[800:].mean())
+        assert np.abs(R[drop_rec + 60:] - rw[k, drop_rec + 60:]).mean() < 0.03
+
+
 def test_turn_open_loop_recordings_in_yaw_invariant_quantities():
     """The 25 recorded turn-ol episodes (160 steps) were called unusable in round 1 ("disagree from step 1").  Read against
     turn_env.py:129-160,271-311 the reason is mostly bookkeeping: every episode starts at a yaw drawn from U(0.2, 6) that the

@@ -48,6 +48,14 @@ def main():
         out[name + "_observ"] = ob[:EPISODES, :n + 1].astype(np.float32)
         out[name + "_reward"] = rw[:EPISODES, :n].astype(np.float32)
         print(name, os.path.basename(prefix), "memory", ob.shape, "->", out[name + "_observ"].shape)
+    # walk-ol through goal, brake and standstill: 1200 steps of the four episodes with the nearest targets (1.0 ... 1.8 m; the
+    # target itself is recovered from the recorded reward, tests/test_pybullet_goldens.py)
+    v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ol")), ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
+    rows = [0, 22, 1, 5]
+    out["walk_ol_long_episodes"] = np.array(rows, np.int32)
+    out["walk_ol_long_action"] = v["memory/Variable_2"][rows, :1200].astype(np.float32)
+    out["walk_ol_long_observ"] = v["memory/Variable_1"][rows, :1201].astype(np.float32)
+    out["walk_ol_long_reward"] = v["memory/Variable_5"][rows, :1200].astype(np.float32)
     # walk-ik: NOT replayable step by step (the gait phase ran on the wall clock, gait_planner.py:108-110), kept for the
     # statistical test of the wall-clock emulation (gait_clock_scale): 300 steps of 6 episodes
     v = tfc.load_variables(tfc.latest_checkpoint(os.path.join(REF, "walk", "ik")), ["memory/Variable_1", "memory/Variable_2", "memory/Variable_5"])
